@@ -1,0 +1,145 @@
+/* phasespace_b200 -- C ABI of the B200-native GENBOD event generator.
+ *
+ * The reference (zfit/phasespace) is pure Python on TensorFlow and has no FFI of its own; its
+ * boundary for this path is the Python API.  This header is the C-ABI layer
+ * underneath the Python mirror of that API: plain pointers and sizes, no torch types.  Every entry
+ * cites the reference interface it replaces (paths relative to /root/reference/src/phasespace).
+ *
+ * Ownership: every device buffer is allocated and owned by the caller; the library keeps no global
+ * state beyond immutable ps_tree objects and a cache of compiled kernels.  Calls are asynchronous on
+ * the stream passed in (a CUstream / cudaStream_t handle; 0 = default stream) and thread-safe.
+ * All functions return 0 on success or a negative PS_E_* code; ps_last_error() (thread local)
+ * describes the failure.  4-vectors are [px, py, pz, E] (kinematics.py:32,45), fp64 throughout.
+ */
+#ifndef PHASESPACE_B200_H_
+#define PHASESPACE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_ABI_VERSION 1
+
+/* mass model of a particle (GenParticle(name, mass): phasespace.py:100-119) */
+#define PS_MASS_FIXED 0 /* float mass: has_fixed_mass (phasespace.py:186-189) */
+#define PS_MASS_GAUSS 1 /* truncated normal: mass_functions.py:16-40, tests/helpers/decays.py:26-37 */
+#define PS_MASS_BW 2    /* Cauchy with gamma = width: mass_functions.py:43-67 */
+#define PS_MASS_RELBW 3 /* relativistic Breit-Wigner: mass_functions.py:70-102 */
+#define PS_MASS_USER 4  /* arbitrary callable, pre-evaluated by the caller into user_masses */
+
+#define PS_E_INVALID -1   /* bad argument / malformed tree (ValueError in the reference) */
+#define PS_E_CUDA -2      /* CUDA runtime failure */
+#define PS_E_COMPILE -3   /* NVRTC failed to specialise the kernel for this tree */
+#define PS_E_FORBIDDEN -4 /* kinematically forbidden decay (phasespace.py:357-363) */
+
+/* generate() flags */
+#define PS_GEN_NORMALIZE 1u /* weights = w / w_max (normalize_weights=True, phasespace.py:713-717) */
+#define PS_GEN_EXACT 2u     /* reference operation order, no FMA (parity / debug variant) */
+
+/* One particle of a decay tree.  The top particle has parent = -1; the children of a particle are
+ * the nodes naming it as parent, in array order (GenParticle.set_children, phasespace.py:191-221). */
+typedef struct ps_node_desc {
+    int32_t parent; /* index into the node array, -1 for the top particle */
+    int32_t kind;   /* PS_MASS_* */
+    double mass;    /* fixed mass, or pole mass of a resonance */
+    double width;   /* resonance width (ignored for PS_MASS_FIXED / PS_MASS_USER) */
+} ps_node_desc;
+
+typedef struct ps_tree ps_tree; /* immutable, opaque */
+
+/* Replaces the tree bookkeeping done at trace time by GenParticle._recursive_generate
+ * (phasespace.py:497-626): validates the tree (>= 2 children per decaying particle,
+ * phasespace.py:213-216; fixed-mass top, phasespace.py:543), assigns output slots in the reference's
+ * dict order (phasespace.py:547-570), the uniform draw order (phasespace.py:344-353,367,444-451),
+ * recurse_stable() minimum masses (phasespace.py:326-333) and, when it is event independent, the
+ * analytic maximum weight (phasespace.py:288-298, 571-625). */
+int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tree** out);
+void ps_tree_destroy(ps_tree* tree);
+
+/* Number of particles in the output (every node except the top) and, for node i, its plane in the
+ * particles buffer (-1 for the top).  Slot order == key order of the reference's output dict. */
+int32_t ps_tree_n_particles(const ps_tree* tree);
+int32_t ps_tree_slot(const ps_tree* tree, int32_t node);
+/* Uniform draws consumed per event (3n-4 per decaying node + one per sampled resonance). */
+int32_t ps_tree_n_draws(const ps_tree* tree);
+/* Number of PS_MASS_USER particles and the user_masses column of node i (-1 if not USER). */
+int32_t ps_tree_n_user(const ps_tree* tree);
+int32_t ps_tree_user_column(const ps_tree* tree, int32_t node);
+/* recurse_stable() of node i: the min_mass handed to its mass function (phasespace.py:349). */
+double ps_tree_min_mass(const ps_tree* tree, int32_t node);
+/* Event-independent w_max, or NaN when it depends on the event (boost_to / resonant leaves). */
+double ps_tree_w_max(const ps_tree* tree);
+/* Canonical C++ type of the tree (the kernel template argument) and whether a kernel for it was
+ * compiled ahead of time (otherwise the first ps_generate JIT-compiles it with NVRTC). */
+const char* ps_tree_signature(const ps_tree* tree);
+int32_t ps_tree_is_aot(const ps_tree* tree, int32_t with_boost, int32_t with_debug_uniforms, uint32_t flags);
+
+/* Replaces GenParticle.generate / _recursive_generate / _generate / _generate_part2
+ * (phasespace.py:628-717, 497-626, 300-397, 399-495) and the rng.uniform calls of random.py:
+ * generates events [first_event, first_event + n_events) of the stream `seed` into device buffers.
+ *   boost_to       NULL (rest frame, phasespace.py:537-541) or device (n_events,4) with boost_rows =
+ *                  n_events, or (1,4) with boost_rows = 1 (phasespace.py:534-535, 697-703); 32-byte aligned
+ *   debug_uniforms NULL (in-kernel Philox4x32-10 keyed on (seed, event index)) or device
+ *                  (n_events, ps_tree_n_draws) uniforms in the reference's draw order (parity mode)
+ *   user_masses    device (n_events, ps_tree_n_user) for PS_MASS_USER particles, else NULL
+ *   weights        device (n_events)
+ *   weights_max    device (n_events) or NULL; written only without PS_GEN_NORMALIZE
+ *   particles      device; plane s (slot s) starts at particles + s*particle_stride doubles and holds
+ *                  (n_events,4) rows; particle_stride >= 4*n_events and a multiple of 4; 32-byte aligned
+ *   stats          NULL or device double[4], caller-zeroed, accumulated atomically:
+ *                  [max w_out, sum w_out, sum w_out^2, max w_max]
+ *   err_flag       device int, caller-zeroed; set to 1 on a forbidden decay */
+int ps_generate(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events, const double* boost_to,
+                int64_t boost_rows, const double* debug_uniforms, const double* user_masses, double* weights,
+                double* weights_max, double* particles, int64_t particle_stride, double* stats, int32_t* err_flag,
+                uint32_t flags, void* stream);
+
+/* As ps_generate but local event i is global event event_index[i] (device int64 array): the second
+ * pass of unweighting regenerates exactly the accepted events. */
+int ps_generate_indexed(const ps_tree* tree, uint64_t seed, const int64_t* event_index, int64_t n_events,
+                        const double* boost_to, int64_t boost_rows, const double* user_masses, double* weights,
+                        double* weights_max, double* particles, int64_t particle_stride, double* stats,
+                        int32_t* err_flag, uint32_t flags, void* stream);
+
+/* Host-buffer end-to-end call (what a numpy user of the reference gets back): generates in chunks on
+ * the device and streams results into HOST memory (pinned memory overlaps copy and compute).
+ * Synchronous.  host_particles plane s starts at host_particles + s*4*n_events. */
+int ps_generate_host(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events,
+                     const double* host_boost_to, int64_t boost_rows, double* host_weights, double* host_weights_max,
+                     double* host_particles, int64_t chunk_events, uint32_t flags);
+
+/* Accept-reject unweighting, deterministic and ordered by event index:
+ *   ps_unweight_mask   recomputes the weights of [first_event, first_event+n_events) (no 4-vectors are
+ *                      formed or stored), draws one extra uniform per event (Philox stream 1) and sets
+ *                      bit (i%32) of mask[i/32] when u * w_bound < w/w_max... see DESIGN.md;
+ *                      tile_counts[t] = accepted events in tile t of 256 events.
+ *   ps_unweight_index  turns mask + exclusive-scanned tile offsets into the sorted list of accepted
+ *                      global event indices (feed to ps_generate_indexed). */
+int ps_unweight_mask(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events, double w_bound,
+                     uint32_t* mask, int32_t* tile_counts, int32_t* err_flag, uint32_t flags, void* stream);
+int ps_unweight_scan(const int32_t* tile_counts, int64_t n_tiles, int64_t* tile_offsets, int64_t* total, void* stream);
+int ps_unweight_index(const uint32_t* mask, const int64_t* tile_offsets, uint64_t first_event, int64_t n_events,
+                      int64_t* event_index, void* stream);
+
+/* Stand-alone resonance sampler, the device implementation behind the callables of
+ * fromdecay/mass_functions.py:31-38, 58-65, 89-100: out[i] ~ kind(mass, width) within
+ * [min_mass[i], max_mass[i]], one Philox draw per event (stream 2). */
+int ps_sample_mass(int32_t kind, double mass, double width, const double* min_mass, const double* max_mass,
+                   int64_t n_events, uint64_t seed, uint64_t first_event, double* out, void* stream);
+
+/* kinematics.py helpers on device (N,4) arrays: lorentz_boost (122-149), mass (93-104). */
+int ps_lorentz_boost(const double* vectors, const double* boost, int64_t boost_rows, int32_t boost_cols,
+                     int64_t n, double* out, void* stream);
+int ps_mass(const double* vectors, int64_t n, double* out, void* stream);
+
+const char* ps_last_error(void);
+int32_t ps_abi_version(void);
+/* Kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t ps_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,796 @@
+// C-ABI implementation (include/phasespace_b200.h): decay-tree compiler, kernel registry (ahead of
+// time + NVRTC), launchers, and the small tree-independent kernels.
+//
+// Host-side counterpart of the bookkeeping the reference does in Python at trace time:
+// GenParticle.set_children validation (phasespace.py:191-221), output-dict order (547-570), draw
+// order (344-353, 367, 444-451), recurse_stable (326-333), _get_w_max / recurse_w_max (288-298,
+// 571-625).  There is deliberately no CPU implementation of the event generation here: without a
+// CUDA device every compute entry point fails with PS_E_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/phasespace_b200.h"
+#include "ps_params.h"
+#include "ps_philox.cuh"
+#include "ps_registry.h"
+#include "ps_samplers.cuh"
+
+#define PS_BLOCK 256
+
+namespace {
+
+thread_local std::string g_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define PS_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t err__ = (expr);                                                                \
+        if (err__ != cudaSuccess) return fail(PS_E_CUDA, "%s: %s", #expr, cudaGetErrorString(err__)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------- registry
+struct KernelKey {
+    std::string sig;
+    int variant, boost, dbg, exact;
+    bool operator<(const KernelKey& o) const {
+        if (sig != o.sig) return sig < o.sig;
+        if (variant != o.variant) return variant < o.variant;
+        if (boost != o.boost) return boost < o.boost;
+        if (dbg != o.dbg) return dbg < o.dbg;
+        return exact < o.exact;
+    }
+};
+
+struct Registry {
+    std::mutex mu;
+    std::map<KernelKey, const void*> aot;
+    std::map<KernelKey, const void*> jit;           // cudaKernel_t handles of NVRTC-built kernels
+    std::map<const void*, int> blocks_per_sm;       // occupancy cache
+};
+Registry& registry() {
+    static Registry r;
+    return r;
+}
+
+}  // namespace
+
+extern "C" void ps_aot_register(const PsAotEntry* table, int n) {
+    Registry& r = registry();
+    std::lock_guard<std::mutex> lock(r.mu);
+    for (int i = 0; i < n; ++i)
+        r.aot[KernelKey{table[i].signature, table[i].variant, table[i].boost, table[i].dbg, table[i].exact}] = table[i].fn;
+}
+
+// ---------------------------------------------------------------------------------- decay tree
+struct ps_tree {
+    int n_nodes = 0;
+    std::vector<ps_node_desc> nodes;
+    std::vector<std::vector<int>> children;
+    std::vector<int> slot, ucol, user_col;
+    std::vector<double> min_mass;
+    int top = -1, n_particles = 0, n_draws = 0, n_user = 0;
+    bool has_grandchildren = false, resonant_leaf = false;
+    double w_max = NAN;
+    std::string signature;
+    PsParams base;  // constant part of the parameter block
+};
+
+namespace {
+
+bool is_sampled(int kind) { return kind == PS_MASS_GAUSS || kind == PS_MASS_BW || kind == PS_MASS_RELBW; }
+
+// phasespace.py:547-570 -- a node's children first, then each decaying child's subtree
+void assign_slots(ps_tree& t, int node, int& next_slot, int& next_col) {
+    const std::vector<int>& ch = t.children[node];
+    for (int c : ch) t.slot[c] = next_slot++;
+    const int n = (int)ch.size();
+    t.ucol[node] = next_col;
+    int sampled = 0;
+    for (int c : ch) sampled += is_sampled(t.nodes[c].kind) ? 1 : 0;
+    next_col += sampled + (n - 2) + 2 * (n - 1);
+    for (int c : ch)
+        if (!t.children[c].empty()) assign_slots(t, c, next_slot, next_col);
+}
+
+// phasespace.py:326-333
+double recurse_stable(const ps_tree& t, int node) {
+    double out = 0.0;
+    for (int c : t.children[node])
+        out = out + (t.nodes[c].kind == PS_MASS_FIXED ? t.nodes[c].mass : recurse_stable(t, c));
+    return out;
+}
+
+std::string emit_signature(const ps_tree& t, int node) {
+    std::string s = "Pt<" + std::to_string(t.slot[node]) + "," + std::to_string(t.nodes[node].kind) + "," +
+                    std::to_string(t.children[node].empty() ? -1 : t.ucol[node]);
+    for (int c : t.children[node]) s += "," + emit_signature(t, c);
+    return s + ">";
+}
+
+double host_pdk(double a, double b, double c) {
+    volatile double x = (a - b - c) * (a + b + c) * (a - b + c) * (a + b - c);
+    return std::sqrt(x) / (2.0 * a);
+}
+// phasespace.py:288-298
+double host_get_w_max(double avail, const std::vector<double>& m) {
+    double emmax = avail + m[0], emmin = 0.0, w = 1.0;
+    for (size_t i = 1; i < m.size(); ++i) {
+        emmin = emmin + m[i - 1];
+        emmax = emmax + m[i];
+        w = w * host_pdk(emmax, emmin, m[i]);
+    }
+    return w;
+}
+void host_acc_leaves(const ps_tree& t, int node, double& s) {
+    for (int c : t.children[node]) {
+        if (t.children[c].empty())
+            s = s + t.nodes[c].mass;
+        else
+            host_acc_leaves(t, c, s);
+    }
+}
+// phasespace.py:590-616
+double host_recurse_w_max(const ps_tree& t, int node, double parent_mass) {
+    double flat = 0.0;
+    host_acc_leaves(t, node, flat);
+    const double avail = parent_mass - flat;
+    std::vector<double> masses;
+    double w = 1.0;
+    for (int c : t.children[node]) {
+        if (!t.children[c].empty()) {
+            double others = 0.0;
+            for (int o : t.children[node]) {
+                if (o == c) continue;
+                if (t.children[o].empty())
+                    others = others + t.nodes[o].mass;
+                else
+                    host_acc_leaves(t, o, others);
+            }
+            w = w * host_recurse_w_max(t, c, parent_mass - others);
+            double own = 0.0;
+            host_acc_leaves(t, c, own);
+            masses.push_back(own);
+        } else {
+            masses.push_back(t.nodes[c].mass);
+        }
+    }
+    return w * host_get_w_max(avail, masses);
+}
+
+}  // namespace
+
+extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tree** out) {
+    if (!nodes || !out || n_nodes < 3) return fail(PS_E_INVALID, "a decay tree needs a top particle and at least 2 children");
+    if (n_nodes - 1 > PS_MAX_SLOTS) return fail(PS_E_INVALID, "decay tree has more than %d particles", PS_MAX_SLOTS);
+    ps_tree* t = new ps_tree();
+    t->n_nodes = n_nodes;
+    t->nodes.assign(nodes, nodes + n_nodes);
+    t->children.resize(n_nodes);
+    t->slot.assign(n_nodes, -1);
+    t->ucol.assign(n_nodes, -1);
+    t->user_col.assign(n_nodes, -1);
+    t->min_mass.assign(n_nodes, 0.0);
+    for (int i = 0; i < n_nodes; ++i) {
+        const int p = nodes[i].parent;
+        if (p == -1) {
+            if (t->top != -1) { delete t; return fail(PS_E_INVALID, "more than one top particle (parent == -1)"); }
+            t->top = i;
+        } else if (p < 0 || p >= n_nodes || p == i) {
+            delete t;
+            return fail(PS_E_INVALID, "node %d has invalid parent %d", i, p);
+        } else {
+            t->children[p].push_back(i);
+        }
+        if (nodes[i].kind < PS_MASS_FIXED || nodes[i].kind > PS_MASS_USER) { delete t; return fail(PS_E_INVALID, "node %d has unknown mass kind %d", i, nodes[i].kind); }
+        if (is_sampled(nodes[i].kind) && !(nodes[i].width > 0.0)) { delete t; return fail(PS_E_INVALID, "node %d: a sampled resonance needs width > 0", i); }
+    }
+    if (t->top < 0) { delete t; return fail(PS_E_INVALID, "no top particle (parent == -1)"); }
+    if (nodes[t->top].kind != PS_MASS_FIXED) { delete t; return fail(PS_E_INVALID, "Cannot use resonance as top particle"); }
+    for (int i = 0; i < n_nodes; ++i)
+        if (t->children[i].size() == 1) { delete t; return fail(PS_E_INVALID, "Have to set at least 2 children, not 1 for a particle to decay"); }
+    if (t->children[t->top].empty()) { delete t; return fail(PS_E_INVALID, "No children have been configured"); }
+    // reachability (rejects cycles / orphans)
+    {
+        std::vector<int> stack{t->top};
+        int seen = 0;
+        std::vector<char> mark(n_nodes, 0);
+        while (!stack.empty()) {
+            int v = stack.back();
+            stack.pop_back();
+            if (mark[v]) continue;
+            mark[v] = 1;
+            ++seen;
+            for (int c : t->children[v]) stack.push_back(c);
+        }
+        if (seen != n_nodes) { delete t; return fail(PS_E_INVALID, "decay tree is not connected"); }
+    }
+    int next_slot = 0, next_col = 0;
+    assign_slots(*t, t->top, next_slot, next_col);
+    t->n_particles = next_slot;
+    t->n_draws = next_col;
+    memset(&t->base, 0, sizeof(PsParams));
+    t->base.mass[0] = nodes[t->top].mass;
+    for (int i = 0; i < n_nodes; ++i) {
+        if (i == t->top) continue;
+        const int s1 = t->slot[i] + 1;
+        t->base.mass[s1] = nodes[i].mass;
+        t->base.width[s1] = nodes[i].width;
+        t->min_mass[i] = recurse_stable(*t, i);
+        t->base.min_mass[s1] = t->min_mass[i];
+        if (nodes[i].kind == PS_MASS_USER) {
+            t->user_col[i] = t->n_user++;
+            t->base.user_col[s1] = t->user_col[i];
+        }
+        if (!t->children[i].empty()) t->has_grandchildren = true;
+        if (t->children[i].empty() && nodes[i].kind != PS_MASS_FIXED) t->resonant_leaf = true;
+    }
+    // user columns follow slot order so that the Python layer can fill them in generation order
+    {
+        std::vector<int> by_slot(t->n_particles, -1);
+        for (int i = 0; i < n_nodes; ++i)
+            if (i != t->top) by_slot[t->slot[i]] = i;
+        int col = 0;
+        for (int s = 0; s < t->n_particles; ++s) {
+            const int i = by_slot[s];
+            if (nodes[i].kind == PS_MASS_USER) {
+                t->user_col[i] = col;
+                t->base.user_col[s + 1] = col++;
+            }
+        }
+    }
+    t->signature = emit_signature(*t, t->top);
+    if (!t->resonant_leaf) {
+        const double M = nodes[t->top].mass;
+        if (t->has_grandchildren) {
+            t->w_max = host_recurse_w_max(*t, t->top, M);
+        } else {
+            std::vector<double> m;
+            double msum = 0.0;
+            bool first = true;
+            for (int c : t->children[t->top]) {
+                m.push_back(nodes[c].mass);
+                msum = first ? nodes[c].mass : msum + nodes[c].mass;
+                first = false;
+            }
+            t->w_max = host_get_w_max(M - msum, m);
+        }
+        t->base.wmax_const = t->w_max;
+        t->base.inv_wmax_const = 1.0 / t->w_max;
+    }
+    *out = t;
+    return 0;
+}
+
+extern "C" void ps_tree_destroy(ps_tree* tree) { delete tree; }
+extern "C" int32_t ps_tree_n_particles(const ps_tree* t) { return t ? t->n_particles : 0; }
+extern "C" int32_t ps_tree_slot(const ps_tree* t, int32_t node) { return (t && node >= 0 && node < t->n_nodes) ? t->slot[node] : -1; }
+extern "C" int32_t ps_tree_n_draws(const ps_tree* t) { return t ? t->n_draws : 0; }
+extern "C" int32_t ps_tree_n_user(const ps_tree* t) { return t ? t->n_user : 0; }
+extern "C" int32_t ps_tree_user_column(const ps_tree* t, int32_t node) { return (t && node >= 0 && node < t->n_nodes) ? t->user_col[node] : -1; }
+extern "C" double ps_tree_min_mass(const ps_tree* t, int32_t node) { return (t && node >= 0 && node < t->n_nodes) ? t->min_mass[node] : NAN; }
+extern "C" double ps_tree_w_max(const ps_tree* t) { return t ? t->w_max : NAN; }
+extern "C" const char* ps_tree_signature(const ps_tree* t) { return t ? t->signature.c_str() : ""; }
+extern "C" const char* ps_last_error(void) { return g_error.c_str(); }
+extern "C" int32_t ps_abi_version(void) { return PS_ABI_VERSION; }
+extern "C" int64_t ps_launch_count(void) { return g_launches.load(); }
+
+extern "C" int32_t ps_tree_is_aot(const ps_tree* t, int32_t with_boost, int32_t with_dbg, uint32_t flags) {
+    if (!t) return 0;
+    Registry& r = registry();
+    std::lock_guard<std::mutex> lock(r.mu);
+    return r.aot.count(KernelKey{t->signature, PS_VARIANT_GENERATE, with_boost ? 1 : 0, with_dbg ? 1 : 0, (flags & PS_GEN_EXACT) ? 1 : 0}) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------- NVRTC JIT
+namespace {
+
+// The kernel headers, embedded at build time (ps_embedded_src.inc is written by build()).
+struct EmbeddedHeader {
+    const char* name;
+    const char* text;
+};
+#include "ps_embedded_src.inc"
+
+typedef int nvrtcResult_t;
+typedef void* nvrtcProgram_t;
+struct Nvrtc {
+    void* handle = nullptr;
+    nvrtcResult_t (*CreateProgram)(nvrtcProgram_t*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult_t (*CompileProgram)(nvrtcProgram_t, int, const char* const*) = nullptr;
+    nvrtcResult_t (*GetProgramLogSize)(nvrtcProgram_t, size_t*) = nullptr;
+    nvrtcResult_t (*GetProgramLog)(nvrtcProgram_t, char*) = nullptr;
+    nvrtcResult_t (*GetCUBINSize)(nvrtcProgram_t, size_t*) = nullptr;
+    nvrtcResult_t (*GetCUBIN)(nvrtcProgram_t, char*) = nullptr;
+    nvrtcResult_t (*DestroyProgram)(nvrtcProgram_t*) = nullptr;
+    const char* (*GetErrorString)(nvrtcResult_t) = nullptr;
+};
+
+Nvrtc* load_nvrtc() {
+    static Nvrtc n;
+    static bool tried = false;
+    if (tried) return n.handle ? &n : nullptr;
+    tried = true;
+    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char* nm : names) {
+        n.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (n.handle) break;
+    }
+    if (!n.handle) return nullptr;
+#define PS_SYM(field, sym) *(void**)(&n.field) = dlsym(n.handle, sym)
+    PS_SYM(CreateProgram, "nvrtcCreateProgram");
+    PS_SYM(CompileProgram, "nvrtcCompileProgram");
+    PS_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    PS_SYM(GetProgramLog, "nvrtcGetProgramLog");
+    PS_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    PS_SYM(GetCUBIN, "nvrtcGetCUBIN");
+    PS_SYM(DestroyProgram, "nvrtcDestroyProgram");
+    PS_SYM(GetErrorString, "nvrtcGetErrorString");
+#undef PS_SYM
+    if (!n.CreateProgram || !n.CompileProgram || !n.GetCUBIN) {
+        n.handle = nullptr;
+        return nullptr;
+    }
+    return &n;
+}
+
+// Specialise ps_kernel.cuh for one tree: returns a cudaKernel_t (usable with cudaLaunchKernel).
+int jit_compile(const KernelKey& key, const void** fn_out) {
+    Nvrtc* rt = load_nvrtc();
+    if (!rt) return fail(PS_E_COMPILE, "tree %s has no ahead-of-time kernel and libnvrtc could not be loaded", key.sig.c_str());
+    std::string src = "#define PS_EXACT " + std::to_string(key.exact) + "\n#include \"ps_kernel.cuh\"\nusing psk::Pt;\n";
+    if (key.variant == PS_VARIANT_GENERATE) {
+        src += "extern \"C\" __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) ps_jit_kernel(const __grid_constant__ PsParams prm) {\n"
+               "  psk::genbod_body<" + key.sig + ", " + (key.boost ? "true" : "false") + ", " + (key.dbg ? "true" : "false") + ">(prm);\n}\n";
+    } else {
+        src += "extern \"C\" __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) ps_jit_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask, int* tile_counts) {\n"
+               "  psk::genbod_mask_body<" + key.sig + ", " + (key.boost ? "true" : "false") + ">(prm, w_bound, mask, tile_counts);\n}\n";
+    }
+    std::vector<const char*> hdr_text, hdr_name;
+    for (const EmbeddedHeader* h = kEmbeddedHeaders; h->name; ++h) {
+        hdr_text.push_back(h->text);
+        hdr_name.push_back(h->name);
+    }
+    nvrtcProgram_t prog = nullptr;
+    nvrtcResult_t rc = rt->CreateProgram(&prog, src.c_str(), "ps_jit.cu", (int)hdr_text.size(), hdr_text.data(), hdr_name.data());
+    if (rc != 0) return fail(PS_E_COMPILE, "nvrtcCreateProgram failed: %s", rt->GetErrorString ? rt->GetErrorString(rc) : "?");
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+    if (key.exact) opts.push_back("--fmad=false");
+    rc = rt->CompileProgram(prog, (int)opts.size(), opts.data());
+    if (rc != 0) {
+        size_t n = 0;
+        std::string log;
+        if (rt->GetProgramLogSize && rt->GetProgramLogSize(prog, &n) == 0 && n > 1) {
+            log.resize(n);
+            rt->GetProgramLog(prog, &log[0]);
+        }
+        rt->DestroyProgram(&prog);
+        return fail(PS_E_COMPILE, "NVRTC failed for tree %s:\n%.1500s", key.sig.c_str(), log.c_str());
+    }
+    size_t n = 0;
+    rt->GetCUBINSize(prog, &n);
+    std::vector<char> cubin(n);
+    rt->GetCUBIN(prog, cubin.data());
+    rt->DestroyProgram(&prog);
+    cudaLibrary_t lib;
+    PS_CUDA(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    cudaKernel_t kern;
+    PS_CUDA(cudaLibraryGetKernel(&kern, lib, "ps_jit_kernel"));
+    *fn_out = (const void*)kern;
+    return 0;
+}
+
+int get_kernel(const ps_tree* t, int variant, int boost, int dbg, int exact, const void** fn) {
+    KernelKey key{t->signature, variant, boost, dbg, exact};
+    Registry& r = registry();
+    std::lock_guard<std::mutex> lock(r.mu);
+    auto it = r.aot.find(key);
+    if (it != r.aot.end()) { *fn = it->second; return 0; }
+    it = r.jit.find(key);
+    if (it != r.jit.end()) { *fn = it->second; return 0; }
+    int rc = jit_compile(key, fn);
+    if (rc == 0) r.jit[key] = *fn;
+    return rc;
+}
+
+// grid = SM count x resident CTAs per SM (a persistent grid-stride kernel), capped by the tile count
+int pick_grid(const void* fn, long long n_events, int* grid) {
+    Registry& r = registry();
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lock(r.mu);
+        auto it = r.blocks_per_sm.find(fn);
+        if (it != r.blocks_per_sm.end()) per_sm = it->second;
+    }
+    int dev = 0, sms = 0;
+    PS_CUDA(cudaGetDevice(&dev));
+    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PS_BLOCK, 0) != cudaSuccess || per_sm < 1) {
+            (void)cudaGetLastError();
+            per_sm = 2;
+        }
+        std::lock_guard<std::mutex> lock(r.mu);
+        r.blocks_per_sm[fn] = per_sm;
+    }
+    const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
+    long long g = (long long)sms * per_sm;
+    if (g > tiles) g = tiles;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+    return 0;
+}
+
+bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+
+int fill_params(const ps_tree* t, PsParams& p, uint64_t seed, uint64_t first_event, const int64_t* event_index,
+                int64_t n_events, const double* boost_to, int64_t boost_rows, const double* dbg_u,
+                const double* user_masses, double* weights, double* weights_max, double* particles,
+                int64_t particle_stride, double* stats, int32_t* err_flag, uint32_t flags) {
+    if (!t) return fail(PS_E_INVALID, "null tree");
+    if (n_events < 0) return fail(PS_E_INVALID, "n_events must be >= 0");
+    if (!err_flag) return fail(PS_E_INVALID, "err_flag must not be NULL");
+    if (boost_to && boost_rows != 1 && boost_rows != n_events)
+        return fail(PS_E_INVALID, "The number of events requested (%lld) doesn't match the boost_to input size of (%lld, 4)", (long long)n_events, (long long)boost_rows);
+    if (boost_to && !aligned32(boost_to)) return fail(PS_E_INVALID, "boost_to must be 32-byte aligned");
+    if (t->n_user > 0 && !user_masses) return fail(PS_E_INVALID, "tree has %d user-mass particles but user_masses is NULL", t->n_user);
+    p = t->base;
+    p.seed = seed;
+    p.first_event = first_event;
+    p.n_events = n_events;
+    p.event_index = (const long long*)event_index;
+    p.boost_to = boost_to;
+    p.boost_stride = (boost_to && boost_rows == n_events && n_events != 1) ? 4 : 0;
+    p.dbg_u = dbg_u;
+    p.dbg_ncols = t->n_draws;
+    p.n_user = t->n_user;
+    p.user_masses = user_masses;
+    p.weights = weights;
+    p.weights_max = weights_max;
+    p.particles = particles;
+    p.particle_stride = particle_stride;
+    p.stats = stats;
+    p.err_flag = err_flag;
+    p.normalize = (flags & PS_GEN_NORMALIZE) ? 1 : 0;
+    return 0;
+}
+
+int launch_generate(const ps_tree* t, PsParams& p, uint32_t flags, void* stream) {
+    if (p.n_events == 0) return 0;
+    if (!p.weights || !p.particles) return fail(PS_E_INVALID, "weights and particles must not be NULL");
+    if (!aligned32(p.particles) || (p.particle_stride & 3) || p.particle_stride < 4 * p.n_events)
+        return fail(PS_E_INVALID, "particles must be 32-byte aligned with particle_stride a multiple of 4 and >= 4*n_events");
+    const void* fn = nullptr;
+    int rc = get_kernel(t, PS_VARIANT_GENERATE, p.boost_to ? 1 : 0, p.dbg_u ? 1 : 0, (flags & PS_GEN_EXACT) ? 1 : 0, &fn);
+    if (rc) return rc;
+    int grid = 1;
+    rc = pick_grid(fn, p.n_events, &grid);
+    if (rc) return rc;
+    void* args[] = {&p};
+    PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, 0, (cudaStream_t)stream));
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int ps_generate(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events,
+                           const double* boost_to, int64_t boost_rows, const double* debug_uniforms,
+                           const double* user_masses, double* weights, double* weights_max, double* particles,
+                           int64_t particle_stride, double* stats, int32_t* err_flag, uint32_t flags, void* stream) {
+    PsParams p;
+    int rc = fill_params(tree, p, seed, first_event, nullptr, n_events, boost_to, boost_rows, debug_uniforms, user_masses,
+                         weights, weights_max, particles, particle_stride, stats, err_flag, flags);
+    if (rc) return rc;
+    return launch_generate(tree, p, flags, stream);
+}
+
+extern "C" int ps_generate_indexed(const ps_tree* tree, uint64_t seed, const int64_t* event_index, int64_t n_events,
+                                   const double* boost_to, int64_t boost_rows, const double* user_masses,
+                                   double* weights, double* weights_max, double* particles, int64_t particle_stride,
+                                   double* stats, int32_t* err_flag, uint32_t flags, void* stream) {
+    if (!event_index && n_events > 0) return fail(PS_E_INVALID, "event_index must not be NULL");
+    PsParams p;
+    int rc = fill_params(tree, p, seed, 0, event_index, n_events, boost_to, boost_rows, nullptr, user_masses, weights,
+                         weights_max, particles, particle_stride, stats, err_flag, flags);
+    if (rc) return rc;
+    return launch_generate(tree, p, flags, stream);
+}
+
+// ---------------------------------------------------------------------------------- host-buffer path
+extern "C" int ps_generate_host(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events,
+                                const double* host_boost_to, int64_t boost_rows, double* host_weights,
+                                double* host_weights_max, double* host_particles, int64_t chunk_events, uint32_t flags) {
+    if (!tree) return fail(PS_E_INVALID, "null tree");
+    if (tree->n_user > 0) return fail(PS_E_INVALID, "ps_generate_host does not take user-mass trees");
+    if (n_events < 0 || !host_weights || !host_particles) return fail(PS_E_INVALID, "bad host buffers");
+    if (host_boost_to && boost_rows != 1 && boost_rows != n_events)
+        return fail(PS_E_INVALID, "The number of events requested (%lld) doesn't match the boost_to input size of (%lld, 4)", (long long)n_events, (long long)boost_rows);
+    if (n_events == 0) return 0;
+    if (chunk_events <= 0) chunk_events = 1 << 22;
+    if (chunk_events > n_events) chunk_events = n_events;
+    chunk_events = (chunk_events + 7) & ~7LL;
+    const int P = tree->n_particles;
+    const bool want_wmax = !(flags & PS_GEN_NORMALIZE) && host_weights_max;
+    const bool per_event_boost = host_boost_to && boost_rows == n_events && n_events != 1;
+    constexpr int NBUF = 2;
+    cudaStream_t streams[NBUF] = {nullptr, nullptr};
+    double* dev[NBUF] = {nullptr, nullptr};
+    int32_t* d_err = nullptr;
+    // per slot: weights | weights_max | particles(P planes) | boost rows
+    const size_t per_slot = (size_t)chunk_events * (size_t)(2 + 4 * P + 4);
+    int rc = 0;
+    auto cleanup = [&]() {
+        for (int b = 0; b < NBUF; ++b) {
+            if (streams[b]) cudaStreamSynchronize(streams[b]);
+            if (dev[b]) cudaFree(dev[b]);
+            if (streams[b]) cudaStreamDestroy(streams[b]);
+        }
+        if (d_err) cudaFree(d_err);
+    };
+#define PS_CUDA_H(expr)                                                                      \
+    do {                                                                                     \
+        cudaError_t err__ = (expr);                                                          \
+        if (err__ != cudaSuccess) {                                                          \
+            rc = fail(PS_E_CUDA, "%s: %s", #expr, cudaGetErrorString(err__));                \
+            cleanup();                                                                       \
+            return rc;                                                                       \
+        }                                                                                    \
+    } while (0)
+    PS_CUDA_H(cudaMalloc(&d_err, sizeof(int32_t)));
+    PS_CUDA_H(cudaMemset(d_err, 0, sizeof(int32_t)));
+    double* d_boost_one = nullptr;
+    for (int b = 0; b < NBUF; ++b) {
+        PS_CUDA_H(cudaStreamCreateWithFlags(&streams[b], cudaStreamNonBlocking));
+        PS_CUDA_H(cudaMalloc(&dev[b], per_slot * sizeof(double)));
+    }
+    int64_t done = 0;
+    for (int it = 0; done < n_events; ++it) {
+        const int b = it % NBUF;
+        const int64_t n = (n_events - done < chunk_events) ? n_events - done : chunk_events;
+        double* d_w = dev[b];
+        double* d_wmax = d_w + chunk_events;
+        double* d_p = d_wmax + chunk_events;
+        double* d_boost = d_p + (size_t)4 * P * chunk_events;
+        const double* boost_arg = nullptr;
+        int64_t rows_arg = 0;
+        if (host_boost_to) {
+            if (per_event_boost) {
+                PS_CUDA_H(cudaMemcpyAsync(d_boost, host_boost_to + 4 * done, (size_t)n * 32, cudaMemcpyHostToDevice, streams[b]));
+                boost_arg = d_boost;
+                rows_arg = n;
+            } else {
+                PS_CUDA_H(cudaMemcpyAsync(d_boost, host_boost_to, 32, cudaMemcpyHostToDevice, streams[b]));
+                boost_arg = d_boost;
+                rows_arg = 1;
+            }
+        }
+        (void)d_boost_one;
+        rc = ps_generate(tree, seed, first_event + (uint64_t)done, n, boost_arg, rows_arg, nullptr, nullptr, d_w,
+                         want_wmax ? d_wmax : nullptr, d_p, 4 * chunk_events, nullptr, d_err, flags, streams[b]);
+        if (rc) { cleanup(); return rc; }
+        PS_CUDA_H(cudaMemcpyAsync(host_weights + done, d_w, (size_t)n * 8, cudaMemcpyDeviceToHost, streams[b]));
+        if (want_wmax) PS_CUDA_H(cudaMemcpyAsync(host_weights_max + done, d_wmax, (size_t)n * 8, cudaMemcpyDeviceToHost, streams[b]));
+        for (int s = 0; s < P; ++s)
+            PS_CUDA_H(cudaMemcpyAsync(host_particles + (size_t)s * 4 * n_events + 4 * done, d_p + (size_t)s * 4 * chunk_events,
+                                      (size_t)n * 32, cudaMemcpyDeviceToHost, streams[b]));
+        done += n;
+        // before reusing the other buffer next iteration, make sure its previous copies are done
+        if (done < n_events) PS_CUDA_H(cudaStreamSynchronize(streams[(it + 1) % NBUF]));
+    }
+    for (int b = 0; b < NBUF; ++b) PS_CUDA_H(cudaStreamSynchronize(streams[b]));
+    int32_t h_err = 0;
+    PS_CUDA_H(cudaMemcpy(&h_err, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    cleanup();
+#undef PS_CUDA_H
+    if (h_err) return fail(PS_E_FORBIDDEN, "Forbidden decay");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- unweighting
+namespace {
+
+// exclusive scan of int32 tile counts into int64 offsets; one CTA, each thread scans a segment
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(const int* counts, long long n, long long* offsets, long long* total) {
+    __shared__ long long seg[1024];
+    const int t = threadIdx.x;
+    const long long per = (n + 1023) / 1024;
+    const long long lo = per * t < n ? per * t : n, hi = per * (t + 1) < n ? per * (t + 1) : n;
+    long long s = 0;
+    for (long long i = lo; i < hi; ++i) s += counts[i];
+    seg[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        long long run = 0;
+        for (int k = 0; k < 1024; ++k) {
+            const long long v = seg[k];
+            seg[k] = run;
+            run += v;
+        }
+        if (total) *total = run;
+    }
+    __syncthreads();
+    long long run = seg[t];
+    for (long long i = lo; i < hi; ++i) {
+        offsets[i] = run;
+        run += counts[i];
+    }
+}
+
+// one warp per 32 events: accepted events write their global index at the scanned position
+__global__ void __launch_bounds__(PS_BLOCK) index_kernel(const unsigned int* mask, const long long* tile_offsets,
+                                                         unsigned long long first_event, long long n, long long* out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (long long tile = blockIdx.x; tile * PS_BLOCK < n; tile += gridDim.x) {
+        const long long w0 = tile * (PS_BLOCK / 32);
+        long long base = tile_offsets[tile];
+        unsigned int word = 0;
+#pragma unroll
+        for (int k = 0; k < PS_BLOCK / 32; ++k) {
+            const unsigned int wk = ((w0 + k) * 32 < n) ? mask[w0 + k] : 0u;
+            if (k < wid) base += __popc(wk);
+            if (k == wid) word = wk;
+        }
+        if (word & (1u << lane)) {
+            const long long i = tile * PS_BLOCK + threadIdx.x;
+            out[base + __popc(word & ((1u << lane) - 1u))] = (long long)(first_event + (unsigned long long)i);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int ps_unweight_mask(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events, double w_bound,
+                                uint32_t* mask, int32_t* tile_counts, int32_t* err_flag, uint32_t flags, void* stream) {
+    if (!tree || !mask || !tile_counts) return fail(PS_E_INVALID, "null argument");
+    if (tree->n_user > 0) return fail(PS_E_INVALID, "unweighting does not take user-mass trees");
+    if (!(w_bound > 0.0)) return fail(PS_E_INVALID, "w_bound must be > 0");
+    PsParams p;
+    int rc = fill_params(tree, p, seed, first_event, nullptr, n_events, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+                         nullptr, 0, nullptr, err_flag, flags | PS_GEN_NORMALIZE);
+    if (rc) return rc;
+    if (n_events == 0) return 0;
+    const void* fn = nullptr;
+    rc = get_kernel(tree, PS_VARIANT_MASK, 0, 0, (flags & PS_GEN_EXACT) ? 1 : 0, &fn);
+    if (rc) return rc;
+    int grid = 1;
+    rc = pick_grid(fn, n_events, &grid);
+    if (rc) return rc;
+    void* args[] = {&p, &w_bound, &mask, &tile_counts};
+    PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, 0, (cudaStream_t)stream));
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+extern "C" int ps_unweight_scan(const int32_t* tile_counts, int64_t n_tiles, int64_t* tile_offsets, int64_t* total, void* stream) {
+    if (!tile_counts || !tile_offsets || n_tiles < 0) return fail(PS_E_INVALID, "null argument");
+    scan_tiles_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tile_counts, n_tiles, (long long*)tile_offsets, (long long*)total);
+    PS_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+extern "C" int ps_unweight_index(const uint32_t* mask, const int64_t* tile_offsets, uint64_t first_event, int64_t n_events,
+                                 int64_t* event_index, void* stream) {
+    if (!mask || !tile_offsets || !event_index) return fail(PS_E_INVALID, "null argument");
+    if (n_events == 0) return 0;
+    int dev = 0, sms = 0;
+    PS_CUDA(cudaGetDevice(&dev));
+    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
+    long long grid = (long long)sms * 8 < tiles ? (long long)sms * 8 : tiles;
+    index_kernel<<<(int)grid, PS_BLOCK, 0, (cudaStream_t)stream>>>(mask, (const long long*)tile_offsets, first_event, n_events, (long long*)event_index);
+    PS_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- small kernels
+namespace {
+
+__global__ void __launch_bounds__(PS_BLOCK) sample_mass_kernel(int kind, double mass, double width, const double* lo,
+                                                               const double* hi, long long n, unsigned long long seed,
+                                                               unsigned long long first_event, double* out) {
+    for (long long i = (long long)blockIdx.x * PS_BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * PS_BLOCK) {
+        const double u = psk::philox_pair(seed, first_event + (unsigned long long)i, 0u, 2u).d0;
+        out[i] = psk::sample_mass(kind, mass, width, lo[i], hi[i], u);
+    }
+}
+
+// kinematics.py:122-149 with per-event zero-boost handling
+__global__ void __launch_bounds__(PS_BLOCK) boost_kernel(const double* v, const double* b, long long b_stride, int b_cols,
+                                                         long long n, double* out) {
+    for (long long i = (long long)blockIdx.x * PS_BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * PS_BLOCK) {
+        double x = v[4 * i], y = v[4 * i + 1], z = v[4 * i + 2], e = v[4 * i + 3];
+        const double bx = b[i * b_stride], by = b[i * b_stride + 1], bz = b[i * b_stride + 2];
+        (void)b_cols;
+        const double b2 = __dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz));
+        if (b2 != 0.0) {
+            const double gamma = 1.0 / sqrt(__dadd_rn(1.0, -b2));
+            const double gamma2 = __dadd_rn(gamma, -1.0) / b2;
+            const double bp = __dadd_rn(__dadd_rn(__dmul_rn(x, bx), __dmul_rn(y, by)), __dmul_rn(z, bz));
+            const double t = __dadd_rn(__dmul_rn(gamma2, bp), __dmul_rn(gamma, e));
+            x = __dadd_rn(x, __dmul_rn(t, bx));
+            y = __dadd_rn(y, __dmul_rn(t, by));
+            z = __dadd_rn(z, __dmul_rn(t, bz));
+            e = __dmul_rn(gamma, __dadd_rn(e, bp));
+        }
+        out[4 * i] = x;
+        out[4 * i + 1] = y;
+        out[4 * i + 2] = z;
+        out[4 * i + 3] = e;
+    }
+}
+
+// kinematics.py:93-104
+__global__ void __launch_bounds__(PS_BLOCK) mass_kernel(const double* v, long long n, double* out) {
+    for (long long i = (long long)blockIdx.x * PS_BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * PS_BLOCK) {
+        const double x = v[4 * i], y = v[4 * i + 1], z = v[4 * i + 2], e = v[4 * i + 3];
+        double s = -__dmul_rn(x, x);
+        s = __dadd_rn(s, -__dmul_rn(y, y));
+        s = __dadd_rn(s, -__dmul_rn(z, z));
+        s = __dadd_rn(s, __dmul_rn(e, e));
+        out[i] = sqrt(s);
+    }
+}
+
+int small_grid(long long n) {
+    long long g = (n + PS_BLOCK - 1) / PS_BLOCK;
+    if (g > 148 * 16) g = 148 * 16;
+    return g < 1 ? 1 : (int)g;
+}
+
+}  // namespace
+
+extern "C" int ps_sample_mass(int32_t kind, double mass, double width, const double* min_mass, const double* max_mass,
+                              int64_t n_events, uint64_t seed, uint64_t first_event, double* out, void* stream) {
+    if (!is_sampled(kind)) return fail(PS_E_INVALID, "ps_sample_mass: kind must be GAUSS, BW or RELBW");
+    if (!(width > 0.0)) return fail(PS_E_INVALID, "ps_sample_mass: width must be > 0");
+    if (!min_mass || !max_mass || !out || n_events < 0) return fail(PS_E_INVALID, "null argument");
+    if (n_events == 0) return 0;
+    sample_mass_kernel<<<small_grid(n_events), PS_BLOCK, 0, (cudaStream_t)stream>>>(kind, mass, width, min_mass, max_mass, n_events, seed, first_event, out);
+    PS_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+extern "C" int ps_lorentz_boost(const double* vectors, const double* boost, int64_t boost_rows, int32_t boost_cols,
+                                int64_t n, double* out, void* stream) {
+    if (!vectors || !boost || !out || n < 0) return fail(PS_E_INVALID, "null argument");
+    if (boost_cols != 3 && boost_cols != 4) return fail(PS_E_INVALID, "boost vector must have 3 or 4 columns");
+    if (boost_rows != 1 && boost_rows != n) return fail(PS_E_INVALID, "boost rows must be 1 or n");
+    if (n == 0) return 0;
+    boost_kernel<<<small_grid(n), PS_BLOCK, 0, (cudaStream_t)stream>>>(vectors, boost, (boost_rows == n && n != 1) ? boost_cols : 0, boost_cols, n, out);
+    PS_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+extern "C" int ps_mass(const double* vectors, int64_t n, double* out, void* stream) {
+    if (!vectors || !out || n < 0) return fail(PS_E_INVALID, "null argument");
+    if (n == 0) return 0;
+    mass_kernel<<<small_grid(n), PS_BLOCK, 0, (cudaStream_t)stream>>>(vectors, n, out);
+    PS_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+}

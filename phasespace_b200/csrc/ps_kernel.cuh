@@ -1,0 +1,690 @@
+// Fused GENBOD / Raubold-Lynch event generator for one decay tree: one event per thread.
+//
+// Replaces, in ONE kernel, everything below GenParticle._recursive_generate in the reference
+// (src/phasespace/phasespace.py:497-626 -> _generate 300-397 -> _generate_part2 399-495 -> pdk 56-71,
+// _get_w_max 288-298; kinematics.py:93-175; random.py) for a whole decay tree.  The tree is a
+// compile-time type (Pt<...> below) so that every particle 4-vector lives in registers; masses and
+// widths are runtime constants in the kernel-parameter block.  The same header is instantiated ahead
+// of time for common trees (ps_aot.cu) and by NVRTC for any other tree (ps_api.cu).
+//
+// Two arithmetic variants, selected per translation unit:
+//   PS_EXACT=1 (compiled with -fmad=false): the reference's operation order, op for op (SURVEY.md
+//              appendix A); differs from the numpy oracle only through sin/cos (<= 2 ulp).
+//   PS_EXACT=0 (default, the product path): algebraically identical but restructured for the B200
+//              fp64 pipe -- reciprocals shared between pdk and the boosts, two-body energies from
+//              invariants instead of square roots, gamma/gamma*beta boosts, sincospi, FMA
+//              contraction.  Agrees with the oracle to ~1e-15 of the parent mass scale.
+//
+// This file must stay NVRTC-clean: no system headers.
+#ifndef PS_KERNEL_CUH_
+#define PS_KERNEL_CUH_
+
+#include "ps_params.h"
+#include "ps_philox.cuh"
+#include "ps_samplers.cuh"
+
+#ifndef PS_EXACT
+#define PS_EXACT 0
+#endif
+#ifndef PS_BLOCK
+#define PS_BLOCK 256
+#endif
+#ifndef PS_MIN_BLOCKS
+#define PS_MIN_BLOCKS 1
+#endif
+
+namespace psk {
+
+// ------------------------------------------------------------------ tiny metaprogramming kit
+template <int... I>
+struct Seq {};
+template <int N, int... I>
+struct MakeSeqT : MakeSeqT<N - 1, N - 1, I...> {};
+template <int... I>
+struct MakeSeqT<0, I...> {
+    using type = Seq<I...>;
+};
+template <int N>
+using MakeSeq = typename MakeSeqT<N>::type;
+
+template <int J, class... Ts>
+struct Nth;
+template <class T, class... Ts>
+struct Nth<0, T, Ts...> {
+    using type = T;
+};
+template <int J, class T, class... Ts>
+struct Nth<J, T, Ts...> : Nth<J - 1, Ts...> {};
+
+// Decay-tree node.  SLOT: output slot of this particle (-1 for the top), in the reference's dict
+// order (phasespace.py:547-570).  KIND: mass model (PS_KIND_*).  UCOL: column of this node's first
+// uniform in the tree-wide draw order (decaying nodes only).  Ch...: children, in declaration order.
+template <int SLOT, int KIND, int UCOL, class... Ch>
+struct Pt {
+    static constexpr int slot = SLOT, kind = KIND, ucol = UCOL, nch = sizeof...(Ch);
+    static constexpr bool sampled = (KIND == PS_KIND_GAUSS || KIND == PS_KIND_BW || KIND == PS_KIND_RELBW);
+    static constexpr int n_below = (0 + ... + (1 + Ch::n_below));
+    static constexpr int n_sampled_children = (0 + ... + (Ch::sampled ? 1 : 0));
+    static constexpr bool resonant_leaf_below =
+        (false || ... || ((Ch::nch == 0 && Ch::kind != PS_KIND_FIXED) || Ch::resonant_leaf_below));
+    static constexpr bool has_grandchildren = (false || ... || (Ch::nch > 0));
+    template <int J>
+    using child = typename Nth<J, Ch...>::type;
+    __host__ __device__ static constexpr int sampled_before(int j) {
+        const bool s[] = {Ch::sampled..., false};
+        int n = 0;
+        for (int i = 0; i < j; ++i) n += s[i] ? 1 : 0;
+        return n;
+    }
+};
+
+// ------------------------------------------------------------------ per-event state
+template <int P, bool DBG>
+struct Ctx {
+    double px[P], py[P], pz[P], en[P], ms[P];
+    unsigned long long seed, event;
+    const double* dbg_row;
+    double stash;
+    bool bad;
+
+    // Draw number COL of this event.  Draws are consumed strictly in column order, so the second
+    // double of each Philox block is simply carried in a register until the next (odd) column.
+    template <int COL>
+    __device__ __forceinline__ double next() {
+        if constexpr (DBG) {
+            return dbg_row[COL];
+        } else if constexpr (COL % 2 == 0) {
+            const Philox2d r = philox_pair(seed, event, COL / 2, 0u);
+            stash = r.d1;
+            return r.d0;
+        } else {
+            return stash;
+        }
+    }
+};
+
+// ------------------------------------------------------------------ kinematics (kinematics.py)
+// kin.mass, kinematics.py:93-104, metric (-,-,-,+) summed left to right
+__device__ __forceinline__ double kin_mass(double x, double y, double z, double e) {
+    double s = -(x * x);
+    s = s + -(y * y);
+    s = s + -(z * z);
+    s = s + e * e;
+    return sqrt(s);
+}
+
+// phasespace.py:56-71 -- CERN 68-15 eq. 9.17, factors in the reference's order
+__device__ __forceinline__ double pdk_x(double a, double b, double c) {
+    return (a - b - c) * (a + b + c) * (a - b + c) * (a + b - c);
+}
+__device__ __forceinline__ double pdk(double a, double b, double c) { return sqrt(pdk_x(a, b, c)) / (2.0 * a); }
+
+// phasespace.py:288-298
+template <int N>
+__device__ __forceinline__ double get_w_max(double avail, const double (&m)[N]) {
+    double emmax = avail + m[0], emmin = 0.0, w_max = 1.0;
+#pragma unroll
+    for (int i = 1; i < N; ++i) {
+        emmin = emmin + m[i - 1];
+        emmax = emmax + m[i];
+        w_max = w_max * pdk(emmax, emmin, m[i]);
+    }
+    return w_max;
+}
+
+// kinematics.py:122-149, reference operation order.  The reference tests b2 == 0 over the whole
+// batch (kinematics.py:147); here it is per event, a superset of the reference's finite behaviour.
+__device__ __forceinline__ void lorentz_boost_exact(double& x, double& y, double& z, double& e, double bx, double by,
+                                                    double bz) {
+    double b2 = bx * bx;
+    b2 = b2 + by * by;
+    b2 = b2 + bz * bz;
+    if (b2 == 0.0) return;
+    const double gamma = 1.0 / sqrt(1.0 - b2);
+    const double gamma2 = (gamma - 1.0) / b2;
+    double bp = x * bx;
+    bp = bp + y * by;
+    bp = bp + z * bz;
+    const double t = gamma2 * bp + gamma * e;
+    x = x + t * bx;
+    y = y + t * by;
+    z = z + t * bz;
+    e = gamma * (e + bp);
+}
+
+template <int K>
+__device__ __forceinline__ void sort_network(double (&r)[K]) {
+#pragma unroll
+    for (int i = 1; i < K; ++i) {
+#pragma unroll
+        for (int j = i; j > 0; --j) {
+            const double a = r[j - 1], b = r[j];
+            r[j - 1] = fmin(a, b);
+            r[j] = fmax(a, b);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ child masses (phasespace.py:335-354)
+template <class Node, int J, class C>
+__device__ __forceinline__ void fixed_sum_one(const PsParams& prm, double& s, bool& first) {
+    using Child = typename Node::template child<J>;
+    if constexpr (Child::kind == PS_KIND_FIXED) {
+        s = first ? prm.mass[Child::slot + 1] : s + prm.mass[Child::slot + 1];
+        first = false;
+    }
+}
+
+template <class Node, int J, class C>
+__device__ __forceinline__ void assign_mass_one(C& c, const PsParams& prm, long long i, double* m, double& max_mass) {
+    using Child = typename Node::template child<J>;
+    constexpr int s1 = Child::slot + 1;
+    if constexpr (Child::kind == PS_KIND_FIXED) {
+        m[J] = prm.mass[s1];
+    } else {
+        double mass;
+        if constexpr (Child::kind == PS_KIND_USER) {
+            mass = prm.user_masses[i * prm.n_user + prm.user_col[s1]];
+        } else {
+            const double u = c.template next<Node::ucol + Node::sampled_before(J)>();
+            mass = sample_mass(Child::kind, prm.mass[s1], prm.width[s1], prm.min_mass[s1], max_mass, u);
+        }
+        max_mass = max_mass - mass;  // phasespace.py:352
+        m[J] = mass;
+    }
+}
+
+template <class Node, class C, int... J>
+__device__ __forceinline__ void assign_masses(C& c, const PsParams& prm, long long i, double M, double* m, Seq<J...>) {
+    double fs = 0.0;
+    bool first = true;
+    (fixed_sum_one<Node, J, C>(prm, fs, first), ...);
+    double max_mass = M - fs;  // phasespace.py:342
+    (assign_mass_one<Node, J, C>(c, prm, i, m, max_mass), ...);
+}
+
+template <int BASE, class C, int... I>
+__device__ __forceinline__ void fetch_draws(C& c, double* s, Seq<I...>) {
+    ((s[I] = c.template next<BASE + I>()), ...);
+}
+
+// ------------------------------------------------------------------ one GENBOD step (phasespace.py:428-494)
+// K is the index of the particle created in this step; AB is the column of its (a, b) pair.
+template <int N, int K, int AB, class C>
+__device__ __forceinline__ void genbod_step_exact(C& c, const double* pd, const double* inv, const double* m, double* x,
+                                                  double* y, double* z, double* e) {
+    x[K] = 0.0;
+    y[K] = -pd[K - 1];
+    z[K] = 0.0;
+    e[K] = sqrt(pd[K - 1] * pd[K - 1] + m[K] * m[K]);
+    const double ua = c.template next<AB>();
+    const double ub = c.template next<AB + 1>();
+    const double cz = 2.0 * ua - 1.0;
+    const double sz = sqrt(1.0 - cz * cz);
+    const double ang = (2.0 * 3.141592653589793) * ub;
+    double sy, cy;
+    sincos(ang, &sy, &cy);
+#pragma unroll
+    for (int j = 0; j <= K; ++j) {
+        const double x0 = x[j], y0 = y[j];
+        const double x1 = cz * x0 - sz * y0;
+        y[j] = sz * x0 + cz * y0;
+        const double z0 = z[j];
+        x[j] = cy * x1 - sy * z0;
+        z[j] = sy * x1 + cy * z0;
+    }
+    if constexpr (K < N - 1) {
+        const double beta = pd[K] / sqrt(pd[K] * pd[K] + inv[K] * inv[K]);
+#pragma unroll
+        for (int j = 0; j <= K; ++j) lorentz_boost_exact(x[j], y[j], z[j], e[j], 0.0, beta, 0.0);
+    }
+}
+
+// Fast variant.  ra[i] = 1/inv[i+1]; esub[k] = energy of the (0..k) subsystem in the next frame.
+template <int N, int K, int AB, class C>
+__device__ __forceinline__ void genbod_step_fast(C& c, const double* pd, const double* ra, const double* enew,
+                                                 const double* esub, double* x, double* y, double* z, double* e) {
+    const double ua = c.template next<AB>();
+    const double ub = c.template next<AB + 1>();
+    const double cz = 2.0 * ua - 1.0;
+    const double sz = sqrt(fma(-cz, cz, 1.0));
+    double sy, cy;
+    sincospi(2.0 * ub, &sy, &cy);
+    const double t = sz * pd[K - 1];
+    if constexpr (K == 1) {
+        // particles 0 and 1 are back to back: (0, +-pd0, 0) rotated
+        x[0] = -(cy * t);
+        y[0] = cz * pd[0];
+        z[0] = -(sy * t);
+        e[0] = esub[0];
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const double x0 = x[j], y0 = y[j], z0 = z[j];
+            const double x1 = cz * x0 - sz * y0;
+            y[j] = sz * x0 + cz * y0;
+            x[j] = cy * x1 - sy * z0;
+            z[j] = sy * x1 + cy * z0;
+        }
+    }
+    x[K] = cy * t;
+    y[K] = -(cz * pd[K - 1]);
+    z[K] = sy * t;
+    e[K] = enew[K];
+    if constexpr (K < N - 1) {
+        // boost along +y into the rest frame of subsystem K+1: gamma = E_sub/inv[K], gamma*beta = pd[K]/inv[K]
+        const double g = esub[K] * ra[K - 1], gb = pd[K] * ra[K - 1];
+#pragma unroll
+        for (int j = 0; j <= K; ++j) {
+            const double y0 = y[j], e0 = e[j];
+            y[j] = fma(g, y0, gb * e0);
+            e[j] = fma(g, e0, gb * y0);
+        }
+    }
+}
+
+template <int N, int AB0, class C, int... KM1>
+__device__ __forceinline__ void genbod_steps_exact(C& c, const double* pd, const double* inv, const double* m, double* x,
+                                                   double* y, double* z, double* e, Seq<KM1...>) {
+    (genbod_step_exact<N, KM1 + 1, AB0 + 2 * KM1>(c, pd, inv, m, x, y, z, e), ...);
+}
+template <int N, int AB0, class C, int... KM1>
+__device__ __forceinline__ void genbod_steps_fast(C& c, const double* pd, const double* ra, const double* enew,
+                                                  const double* esub, double* x, double* y, double* z, double* e,
+                                                  Seq<KM1...>) {
+    (genbod_step_fast<N, KM1 + 1, AB0 + 2 * KM1>(c, pd, ra, enew, esub, x, y, z, e), ...);
+}
+
+template <class Node, class C, int... J>
+__device__ __forceinline__ void store_children(C& c, const double* m, const double* x, const double* y, const double* z,
+                                               const double* e, Seq<J...>) {
+    ((c.px[Node::template child<J>::slot] = x[J], c.py[Node::template child<J>::slot] = y[J],
+      c.pz[Node::template child<J>::slot] = z[J], c.en[Node::template child<J>::slot] = e[J],
+      c.ms[Node::template child<J>::slot] = m[J]),
+     ...);
+}
+
+template <class Node, bool REST, class C>
+__device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long i, double ppx, double ppy, double ppz,
+                                           double pe);
+
+template <class Node, int J, class C>
+__device__ __forceinline__ void recurse_child(C& c, const PsParams& prm, long long i, double& w) {
+    using Child = typename Node::template child<J>;
+    if constexpr (Child::nch > 0) {
+        constexpr int s = Child::slot;
+        w = w * gen_node<Child, false>(c, prm, i, c.px[s], c.py[s], c.pz[s], c.en[s]);  // phasespace.py:555-568
+    }
+}
+template <class Node, class C, int... J>
+__device__ __forceinline__ void recurse_children(C& c, const PsParams& prm, long long i, double& w, Seq<J...>) {
+    (recurse_child<Node, J>(c, prm, i, w), ...);
+}
+
+// ------------------------------------------------------------------ one decay node
+// GenParticle._generate + _generate_part2 (phasespace.py:300-495) for the node, then the recursion of
+// _recursive_generate (phasespace.py:555-570).  (ppx,ppy,ppz,pe) is the parent's 4-vector in the
+// output frame; REST says it is (0,0,0,M) so the final boost is the identity.  Returns the product
+// of the two-body momenta of this node and of every decaying node below it.
+template <class Node, bool REST, class C>
+__device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long i, double ppx, double ppy, double ppz,
+                                           double pe) {
+    constexpr int N = Node::nch;
+    constexpr int NS = Node::n_sampled_children;
+    constexpr int SORT0 = Node::ucol + NS;       // first of the N-2 sorted uniforms
+    constexpr int AB0 = Node::ucol + NS + N - 2;  // first (a,b) pair
+    static_assert(N >= 2, "a decaying particle needs at least two children");
+
+    double M;
+    if constexpr (REST) {
+        M = prm.mass[0];
+    } else if constexpr (PS_EXACT || Node::slot < 0) {
+        M = kin_mass(ppx, ppy, ppz, pe);  // phasespace.py:322
+    } else {
+        M = c.ms[Node::slot];  // fast: the mass this particle was generated with
+    }
+
+    double m[N];
+    assign_masses<Node>(c, prm, i, M, m, MakeSeq<N>{});
+    double msum = m[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) msum = msum + m[j];
+    const double avail = M - msum;    // phasespace.py:357
+    if (!(avail >= 0.0)) c.bad = true;  // "Forbidden decay", phasespace.py:358-363
+
+    double r[N];
+    r[0] = 0.0;
+    r[N - 1] = 1.0;
+    if constexpr (N > 2) {  // phasespace.py:367-375
+        double s[N - 2];
+        fetch_draws<SORT0>(c, s, MakeSeq<N - 2>{});
+        sort_network<N - 2>(s);
+#pragma unroll
+        for (int j = 0; j < N - 2; ++j) r[j + 1] = s[j];
+    }
+    double inv[N];
+    {
+        double sum_ = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {  // phasespace.py:379-384
+            sum_ = sum_ + m[j];
+            inv[j] = r[j] * avail + sum_;
+        }
+    }
+
+    double x[N], y[N], z[N], e[N];
+    double wn;
+#if PS_EXACT
+    {
+        double pd[N - 1];
+#pragma unroll
+        for (int j = 0; j < N - 1; ++j) pd[j] = pdk(inv[j + 1], inv[j], m[j + 1]);  // phasespace.py:404-411
+        wn = pd[0];
+#pragma unroll
+        for (int j = 1; j < N - 1; ++j) wn = wn * pd[j];  // phasespace.py:412
+        x[0] = 0.0;
+        y[0] = pd[0];
+        z[0] = 0.0;
+        e[0] = sqrt(pd[0] * pd[0] + m[0] * m[0]);  // phasespace.py:414-426
+        genbod_steps_exact<N, AB0>(c, pd, inv, m, x, y, z, e, MakeSeq<N - 1>{});
+        if constexpr (!REST) {  // phasespace.py:365, 389-391
+            const double bx = ppx / pe, by = ppy / pe, bz = ppz / pe;
+#pragma unroll
+            for (int j = 0; j < N; ++j) lorentz_boost_exact(x[j], y[j], z[j], e[j], bx, by, bz);
+        }
+    }
+#else
+    {
+        double pd[N - 1], ra[N - 1], enew[N], esub[N - 1];
+#pragma unroll
+        for (int j = 0; j < N - 1; ++j) {
+            const double a = inv[j + 1], b = inv[j], cc = m[j + 1];
+            const double amb = a - b, apb = a + b;
+            const double xx = (amb - cc) * (apb + cc) * (amb + cc) * (apb - cc);
+            ra[j] = 1.0 / a;
+            const double hra = 0.5 * ra[j];
+            pd[j] = sqrt(xx) * hra;
+            enew[j + 1] = fma(amb, apb, cc * cc) * hra;  // (a^2 + c^2 - b^2) / 2a
+            esub[j] = a - enew[j + 1];
+        }
+        wn = pd[0];
+#pragma unroll
+        for (int j = 1; j < N - 1; ++j) wn = wn * pd[j];
+        genbod_steps_fast<N, AB0>(c, pd, ra, enew, esub, x, y, z, e, MakeSeq<N - 1>{});
+        if constexpr (!REST) {
+            // boost by the parent: u = gamma*beta = p/M, gamma = E/M;  p' = p + (u.p/(gamma+1) + E) u ; E' = gamma E + u.p
+            const double rM = 1.0 / M;
+            const double ux = ppx * rM, uy = ppy * rM, uz = ppz * rM, g = pe * rM;
+            const double g1 = 1.0 / (g + 1.0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double up = fma(ux, x[j], fma(uy, y[j], uz * z[j]));
+                const double t = fma(up, g1, e[j]);
+                x[j] = fma(t, ux, x[j]);
+                y[j] = fma(t, uy, y[j]);
+                z[j] = fma(t, uz, z[j]);
+                e[j] = fma(g, e[j], up);
+            }
+        }
+    }
+#endif
+    store_children<Node>(c, m, x, y, z, e, MakeSeq<N>{});
+    recurse_children<Node>(c, prm, i, wn, MakeSeq<N>{});
+    return wn;
+}
+
+// ------------------------------------------------------------------ tree-level maximum weight
+// recurse_w_max, phasespace.py:571-625: leaf masses only, flattened depth first.
+template <class Node, class C>
+__device__ __forceinline__ void acc_leaves(const C& c, double& s);
+template <class Node, int J, class C>
+__device__ __forceinline__ void acc_leaves_child(const C& c, double& s) {
+    using Child = typename Node::template child<J>;
+    if constexpr (Child::nch == 0) {
+        s = s + c.ms[Child::slot];
+    } else {
+        acc_leaves<Child>(c, s);
+    }
+}
+template <class Node, class C, int... J>
+__device__ __forceinline__ void acc_leaves_seq(const C& c, double& s, Seq<J...>) {
+    (acc_leaves_child<Node, J>(c, s), ...);
+}
+template <class Node, class C>
+__device__ __forceinline__ void acc_leaves(const C& c, double& s) {
+    acc_leaves_seq<Node>(c, s, MakeSeq<Node::nch>{});
+}
+template <class Node, int SKIP, class C, int... J>
+__device__ __forceinline__ void acc_leaves_except(const C& c, double& s, Seq<J...>) {
+    ((J != SKIP ? acc_leaves_child<Node, J>(c, s) : (void)0), ...);
+}
+
+template <class Node, class C>
+__device__ __forceinline__ double recurse_w_max(const C& c, double parent_mass);
+
+template <class Node, int J, class C>
+__device__ __forceinline__ void w_max_child(const C& c, double parent_mass, double* masses, double& w_max) {
+    using Child = typename Node::template child<J>;
+    if constexpr (Child::nch > 0) {
+        double others = 0.0;
+        acc_leaves_except<Node, J>(c, others, MakeSeq<Node::nch>{});
+        w_max = w_max * recurse_w_max<Child>(c, parent_mass - others);
+        double own = 0.0;
+        acc_leaves<Child>(c, own);
+        masses[J] = own;
+    } else {
+        masses[J] = c.ms[Child::slot];
+    }
+}
+template <class Node, class C, int... J>
+__device__ __forceinline__ void w_max_children(const C& c, double parent_mass, double* masses, double& w_max, Seq<J...>) {
+    (w_max_child<Node, J>(c, parent_mass, masses, w_max), ...);
+}
+template <class Node, class C>
+__device__ __forceinline__ double recurse_w_max(const C& c, double parent_mass) {
+    constexpr int N = Node::nch;
+    double flat = 0.0;
+    acc_leaves<Node>(c, flat);
+    const double avail = parent_mass - flat;
+    double masses[N];
+    double w_max = 1.0;
+    w_max_children<Node>(c, parent_mass, masses, w_max, MakeSeq<N>{});
+    return w_max * get_w_max<N>(avail, masses);
+}
+
+template <class Node, class C, int... J>
+__device__ __forceinline__ double node_w_max(const C& c, double M, Seq<J...>) {
+    constexpr int N = Node::nch;
+    const double m[N] = {c.ms[Node::template child<J>::slot]...};
+    double msum = m[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) msum = msum + m[j];
+    return get_w_max<N>(M - msum, m);
+}
+
+// ------------------------------------------------------------------ stores
+// One 256-bit store per particle per thread: a warp writes 32 consecutive 32-byte rows = 1 KiB
+// contiguous, i.e. eight full 128-byte lines per instruction (STG.E.ENL2.256 on sm_100a).
+__device__ __forceinline__ void store_row(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void load_row(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+template <class C, int... S>
+__device__ __forceinline__ void store_particles(const C& c, double* base, long long stride, Seq<S...>) {
+    (store_row(base + S * stride, c.px[S], c.py[S], c.pz[S], c.en[S]), ...);
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------ the kernel
+// Grid-stride over tiles of PS_BLOCK events; the host launches (SM count x resident CTAs) blocks.
+template <class Tree, bool BOOST, bool DBG>
+__device__ __forceinline__ void genbod_body(const PsParams& prm) {
+    constexpr int P = Tree::n_below;
+    constexpr bool WMAX_PER_EVENT = BOOST || Tree::resonant_leaf_below;
+    static_assert(P <= PS_MAX_SLOTS, "decay tree too large");
+
+    double st_max = 0.0, st_sum = 0.0, st_sum2 = 0.0, st_wmax = 0.0;
+    bool bad_any = false;
+    const long long n = prm.n_events;
+    for (long long tile = blockIdx.x; tile * PS_BLOCK < n; tile += gridDim.x) {
+        const long long i = tile * PS_BLOCK + threadIdx.x;
+        if (i < n) {
+            Ctx<P, DBG> c;
+            c.seed = prm.seed;
+            c.event = prm.event_index ? (unsigned long long)prm.event_index[i] : prm.first_event + (unsigned long long)i;
+            c.dbg_row = DBG ? prm.dbg_u + i * prm.dbg_ncols : nullptr;
+            c.stash = 0.0;
+            c.bad = false;
+            double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
+            if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
+            const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
+            double w_max;
+            if constexpr (WMAX_PER_EVENT) {
+                const double M = BOOST ? kin_mass(bx, by, bz, be) : prm.mass[0];
+                if constexpr (Tree::has_grandchildren)
+                    w_max = recurse_w_max<Tree>(c, M);  // phasespace.py:571-625
+                else
+                    w_max = node_w_max<Tree>(c, M, MakeSeq<Tree::nch>{});  // phasespace.py:364
+            } else {
+                w_max = prm.wmax_const;
+            }
+            double w_out = w;
+            if (prm.normalize) {  // phasespace.py:713-717
+#if PS_EXACT
+                w_out = w / w_max;
+#else
+                w_out = WMAX_PER_EVENT ? w / w_max : w * prm.inv_wmax_const;
+#endif
+            } else if (prm.weights_max) {
+                prm.weights_max[i] = w_max;
+            }
+            prm.weights[i] = w_out;
+            store_particles(c, prm.particles + i * 4, prm.particle_stride, MakeSeq<P>{});
+            bad_any |= c.bad;
+            st_max = fmax(st_max, w_out);
+            st_sum += w_out;
+            st_sum2 += w_out * w_out;
+            st_wmax = fmax(st_wmax, w_max);
+        }
+    }
+    if (bad_any) *prm.err_flag = PS_ERR_FORBIDDEN;
+    if (prm.stats) {  // epilogue: warp shuffle -> shared -> one atomic per CTA
+        __shared__ double red[4][PS_BLOCK / 32];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        st_max = warp_max(st_max);
+        st_sum = warp_sum(st_sum);
+        st_sum2 = warp_sum(st_sum2);
+        st_wmax = warp_max(st_wmax);
+        if (lane == 0) {
+            red[0][wid] = st_max;
+            red[1][wid] = st_sum;
+            red[2][wid] = st_sum2;
+            red[3][wid] = st_wmax;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            const bool in = lane < PS_BLOCK / 32;
+            st_max = warp_max(in ? red[0][lane] : 0.0);
+            st_sum = warp_sum(in ? red[1][lane] : 0.0);
+            st_sum2 = warp_sum(in ? red[2][lane] : 0.0);
+            st_wmax = warp_max(in ? red[3][lane] : 0.0);
+            if (lane == 0) {
+                // weights are >= 0, so their bit patterns order like unsigned integers
+                atomicMax((unsigned long long*)&prm.stats[0], (unsigned long long)__double_as_longlong(st_max));
+                atomicAdd(&prm.stats[1], st_sum);
+                atomicAdd(&prm.stats[2], st_sum2);
+                atomicMax((unsigned long long*)&prm.stats[3], (unsigned long long)__double_as_longlong(st_wmax));
+            }
+        }
+    }
+}
+
+// EXACT only distinguishes the symbol names of the two arithmetic variants (it must equal PS_EXACT).
+template <class Tree, bool BOOST, bool DBG, int EXACT>
+__global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) genbod_kernel(const __grid_constant__ PsParams prm) {
+    static_assert(EXACT == PS_EXACT, "variant tag must match the translation unit");
+    genbod_body<Tree, BOOST, DBG>(prm);
+}
+
+// ------------------------------------------------------------------ unweighting, pass 1
+// Recomputes the event weights only (the rotations, boosts and their draws are dead code here and
+// are eliminated), draws one acceptance uniform per event from Philox stream 1 and records
+// accept = (u * w_bound < w / w_max) as one bit per event plus a per-tile count.  Together with
+// ps_unweight_scan / ps_unweight_index this yields the accepted events ordered by event index,
+// independent of grid size or GPU count; ps_generate_indexed then regenerates only those.
+template <class Tree, bool BOOST>
+__device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_bound, unsigned int* mask,
+                                                 int* tile_counts) {
+    constexpr int P = Tree::n_below;
+    constexpr bool WMAX_PER_EVENT = BOOST || Tree::resonant_leaf_below;
+    __shared__ int warp_counts[PS_BLOCK / 32];
+    const long long n = prm.n_events;
+    bool bad_any = false;
+    for (long long tile = blockIdx.x; tile * PS_BLOCK < n; tile += gridDim.x) {
+        const long long i = tile * PS_BLOCK + threadIdx.x;
+        bool accept = false;
+        if (i < n) {
+            Ctx<P, false> c;
+            c.seed = prm.seed;
+            c.event = prm.first_event + (unsigned long long)i;
+            c.dbg_row = nullptr;
+            c.stash = 0.0;
+            c.bad = false;
+            double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
+            if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
+            const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
+            double w_max;
+            if constexpr (WMAX_PER_EVENT) {
+                const double M = BOOST ? kin_mass(bx, by, bz, be) : prm.mass[0];
+                if constexpr (Tree::has_grandchildren)
+                    w_max = recurse_w_max<Tree>(c, M);
+                else
+                    w_max = node_w_max<Tree>(c, M, MakeSeq<Tree::nch>{});
+            } else {
+                w_max = prm.wmax_const;
+            }
+            const double u = philox_pair(prm.seed, c.event, 0u, 1u).d0;
+            accept = u * w_bound * w_max < w;
+            bad_any |= c.bad;
+        }
+        const unsigned int word = __ballot_sync(0xffffffffu, accept);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) {
+            const long long wi = tile * (PS_BLOCK / 32) + wid;
+            if (wi * 32 < n) mask[wi] = word;
+            warp_counts[wid] = __popc(word);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int total = 0;
+#pragma unroll
+            for (int k = 0; k < PS_BLOCK / 32; ++k) total += warp_counts[k];
+            tile_counts[tile] = total;
+        }
+        __syncthreads();
+    }
+    if (bad_any) *prm.err_flag = PS_ERR_FORBIDDEN;
+}
+
+template <class Tree, bool BOOST, int EXACT>
+__global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS)
+    genbod_mask_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask, int* tile_counts) {
+    static_assert(EXACT == PS_EXACT, "variant tag must match the translation unit");
+    genbod_mask_body<Tree, BOOST>(prm, w_bound, mask, tile_counts);
+}
+
+}  // namespace psk
+#endif

@@ -1,0 +1,48 @@
+/* Kernel parameter block shared by the AOT kernels, the NVRTC-compiled kernels and the host
+ * launcher.  Plain C so that NVRTC can include it without any system header. */
+#ifndef PS_PARAMS_H_
+#define PS_PARAMS_H_
+
+#define PS_MAX_SLOTS 40 /* particles in one decay tree, excluding the top */
+
+/* mass-model kinds (mirrors include/phasespace_b200.h) */
+#define PS_KIND_FIXED 0
+#define PS_KIND_GAUSS 1 /* truncated normal: zfit Gauss / tfp TruncatedNormal (mass_functions.py:16-40) */
+#define PS_KIND_BW 2    /* Cauchy, gamma = width (mass_functions.py:43-67) */
+#define PS_KIND_RELBW 3 /* relativistic Breit-Wigner density in the mass (mass_functions.py:70-102) */
+#define PS_KIND_USER 4  /* per-event masses supplied by the caller (arbitrary Python callables) */
+
+#define PS_ERR_FORBIDDEN 1 /* available_mass < 0 or NaN: "Forbidden decay" (phasespace.py:357-363) */
+
+typedef struct PsParams {
+    /* index = slot + 1; entry 0 is the top particle */
+    double mass[PS_MAX_SLOTS + 1];     /* fixed mass, or pole mass of a resonance */
+    double width[PS_MAX_SLOTS + 1];    /* resonance width (0 for fixed) */
+    double min_mass[PS_MAX_SLOTS + 1]; /* recurse_stable(): sum of fixed masses below (phasespace.py:326-333) */
+    int user_col[PS_MAX_SLOTS + 1];    /* column in user_masses for PS_KIND_USER */
+
+    double wmax_const;     /* event-independent maximum weight (rest frame, fixed leaf masses) */
+    double inv_wmax_const; /* its reciprocal */
+
+    unsigned long long seed;
+    unsigned long long first_event; /* global index of local event 0: the Philox counter */
+    long long n_events;
+
+    const long long* event_index; /* optional: local event i generates global event event_index[i] */
+    const double* boost_to;       /* optional (n,4) or (1,4) [px,py,pz,E] */
+    long long boost_stride;       /* 4 for per-event rows, 0 to broadcast one row */
+    const double* dbg_u;          /* debug mode: (n_events, dbg_ncols) uniforms in reference draw order */
+    int dbg_ncols;
+    int n_user;
+    const double* user_masses; /* (n_events, n_user) */
+
+    double* weights;           /* (n) */
+    double* weights_max;       /* (n) or NULL */
+    double* particles;         /* (P, particle_stride/4, 4) */
+    long long particle_stride; /* doubles between two particle planes */
+    double* stats;             /* NULL or [max w_out, sum w_out, sum w_out^2, max w_max] */
+    int* err_flag;
+    int normalize; /* 1: weights = w / w_max ; 0: weights = w and weights_max = w_max */
+} PsParams;
+
+#endif

@@ -1,0 +1,165 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerance (BASELINE.json north_star): 1e-12 relative.  Weights are compared relatively; momentum
+components cross zero, so 4-vectors are compared as |delta| / M_top.
+Both arithmetic variants are checked: ``exact`` (reference operation order) and the default fast one.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import genbod_numpy as orc
+from oracle.philox import uniform_table
+
+from .helpers import decays as D
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+N = 20000
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _compare(desc, n, *, exact, use_rng, boost=None, normalize=True, seed=1234, tol=TOL):
+    gen, tree = D.to_gen(desc), D.to_oracle(desc)
+    draws = uniform_table(seed, 0, n, orc.n_draws(tree))
+    boost_np = None if boost is None else np.asarray(boost, dtype=np.float64)
+    ref = orc.generate(tree, n, draws, boost_to=boost_np, normalize_weights=normalize)
+    kwargs = dict(boost_to=None if boost is None else torch.as_tensor(boost_np), normalize_weights=normalize, exact=exact)
+    if use_rng:
+        got = gen.generate(n, seed=seed, **kwargs)
+    else:
+        got = gen.generate(n, debug_uniforms=torch.as_tensor(draws), **kwargs)
+    scale = float(desc[1]) if boost is None else float(np.max(boost_np[:, 3]))
+    assert list(got[-1].keys()) == orc.output_names(tree)
+    np.testing.assert_allclose(_np(got[0]), ref[0], rtol=tol, atol=0)
+    if not normalize:
+        np.testing.assert_allclose(_np(got[1]), ref[1], rtol=tol, atol=0)
+    worst = 0.0
+    for name, vec in ref[-1].items():
+        worst = max(worst, float(np.max(np.abs(_np(got[-1][name]) - vec))) / scale)
+    assert worst <= tol, worst
+    return worst
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("n_body", [2, 3, 4, 5, 7, 10])
+def test_flat_debug_uniforms(n_body, exact):
+    _compare(D.flat_desc(n_body), N, exact=exact, use_rng=False)
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("n_body", [2, 3, 4, 10])
+def test_flat_inkernel_philox(n_body, exact):
+    """Normal mode: the in-kernel Philox stream equals the oracle's table bit for bit, so the events agree too."""
+    _compare(D.flat_desc(n_body), N, exact=exact, use_rng=True, seed=77)
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+def test_mixed_masses_unnormalized(exact):
+    desc = D.flat_desc(4, masses=[D.KAON_MASS, D.PION_MASS, 0.0, 105.6583755])
+    _compare(desc, N, exact=exact, use_rng=False, normalize=False)
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("kind", ["fixed", "gauss", "bw", "relbw"])
+def test_kstar_gamma(kind, exact):
+    desc = D.kstar_gamma_desc(kind) if kind != "fixed" else D.kstar_gamma_desc("fixed", 0.0)
+    # resonance masses go through libm vs CUDA normcdfinv/atan/tan/log: allow a little more
+    _compare(desc, N, exact=exact, use_rng=False, tol=5e-12 if kind != "fixed" else TOL)
+    _compare(desc, N, exact=exact, use_rng=True, normalize=False, tol=5e-12 if kind != "fixed" else TOL)
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("kinds", [("fixed", "fixed"), ("gauss", "gauss"), ("relbw", "relbw"), ("bw", "gauss")])
+def test_k1_gamma(kinds, exact):
+    _compare(D.k1_gamma_desc(*kinds), N, exact=exact, use_rng=False, tol=5e-12)
+
+
+def _fonll_like_boost(n, mass, seed=1234):
+    """Synthetic stand-in for tests/helpers/rapidsim.py:46-51 of the reference (MeV)."""
+    rng = np.random.default_rng(seed)
+    pt = 1000.0 * rng.exponential(5.0, n)
+    eta = rng.uniform(2.0, 5.0, n)
+    phi = rng.uniform(0.0, 2 * np.pi, n)
+    px, py, pz = pt * np.cos(phi), pt * np.sin(phi), pt * np.sinh(eta)
+    return np.stack([px, py, pz, np.sqrt(px * px + py * py + pz * pz + mass * mass)], axis=1)
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+def test_boost_to_per_event(exact):
+    boost = _fonll_like_boost(N, D.B0_MASS)
+    # the boosted frame multiplies rounding errors by gamma ~ E/M: compare on the energy scale
+    _compare(D.flat_desc(4), N, exact=exact, use_rng=False, boost=boost, tol=1e-11)
+    _compare(D.kstar_gamma_desc("gauss"), N, exact=exact, use_rng=True, boost=boost, normalize=False, tol=1e-11)
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+def test_boost_to_broadcast(exact):
+    boost = _fonll_like_boost(1, D.B0_MASS, seed=5)
+    _compare(D.flat_desc(3), N, exact=exact, use_rng=False, boost=boost, tol=1e-11)
+
+
+def test_sharding_is_bit_identical():
+    """Contiguous index ranges generated separately equal the single launch bit for bit."""
+    gen = D.to_gen(D.flat_desc(3))
+    comp = gen.compile()
+    n = 100_003
+    w, _, p, _ = comp.launch(n, seed=99, first_event=0)
+    cuts = [0, 1, 255, 256, 257, 40_000, 77_777, n]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        w2, _, p2, _ = comp.launch(hi - lo, seed=99, first_event=lo)
+        assert torch.equal(w2, w[lo:hi])
+        assert torch.equal(p2, p[:, lo:hi])
+
+
+def test_chain_sharding_is_bit_identical():
+    comp = D.to_gen(D.kstar_gamma_desc("relbw")).compile()
+    n = 30_001
+    w, _, p, _ = comp.launch(n, seed=5)
+    w2, _, p2, _ = comp.launch(n - 12_345, seed=5, first_event=12_345)
+    assert torch.equal(w2, w[12_345:]) and torch.equal(p2, p[:, 12_345:])
+
+
+def test_user_callable_split_path():
+    """A plain Python callable as mass function: evaluated on the device first, then fed per event."""
+    from phasespace_b200 import GenParticle
+
+    n = 5000
+
+    def kstar_mass(min_mass, max_mass, n_events):
+        assert min_mass.shape == (n_events,) and max_mass.shape == (n_events,)
+        assert torch.allclose(min_mass, torch.full_like(min_mass, D.KAON_MASS + D.PION_MASS))
+        assert torch.allclose(max_mass, torch.full_like(max_mass, D.B0_MASS))
+        return torch.linspace(700.0, 1100.0, n_events, dtype=torch.float64, device=min_mass.device)
+
+    gen = GenParticle("B0", D.B0_MASS).set_children(
+        GenParticle("K*0", kstar_mass).set_children(GenParticle("K+", D.KAON_MASS), GenParticle("pi-", D.PION_MASS)),
+        GenParticle("gamma", 0.0),
+    )
+    tree = D.to_oracle(D.kstar_gamma_desc("fixed", 0.0))
+    tree.children[0].kind = orc.USER
+    masses = np.linspace(700.0, 1100.0, n)
+    draws = uniform_table(3, 0, n, orc.n_draws(tree))
+    ref_w, ref_p = orc.generate(tree, n, draws, user_masses={"K*0": masses})
+    w, p = gen.generate(n, debug_uniforms=torch.as_tensor(draws))
+    np.testing.assert_allclose(_np(w), ref_w, rtol=TOL)
+    for name in ref_p:
+        assert np.max(np.abs(_np(p[name]) - ref_p[name])) / D.B0_MASS <= TOL
+    m_kst = np.sqrt(np.maximum(_np(p["K*0"])[:, 3] ** 2 - (_np(p["K*0"])[:, :3] ** 2).sum(1), 0))
+    np.testing.assert_allclose(m_kst, masses, rtol=1e-9)
+
+
+def test_forbidden_decay_raises():
+    import phasespace_b200 as ps
+
+    with pytest.raises(ps.ForbiddenDecayError):
+        ps.nbody_decay(300.0, [139.57018] * 3).generate(10)
+    # per-event: a boost_to whose invariant mass is too small for the children
+    boost = np.array([[0.0, 0.0, 100.0, 250.0]])
+    with pytest.raises(ps.ForbiddenDecayError):
+        ps.nbody_decay(D.B0_MASS, [139.57018] * 3).generate(10, boost_to=boost)
