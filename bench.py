@@ -208,6 +208,7 @@ def run_b200(args, rank, local_rank, world):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    stats.zero_()
     launches0 = _lib.lib.ps_launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -229,6 +230,7 @@ def run_b200(args, rank, local_rank, world):
         dist.all_reduce(kernel_ms, op=dist.ReduceOp.MAX)
     total_ms, kernel_ms = float(total_ms.item()), float(kernel_ms.item())
     clocks = sampler.summary(wall0, wall1)
+    gstats = stats.clone()  # statistics of exactly the timed launches
     if clocks["samples"] < 3:  # timed region shorter than the sampling period: probe the same kernel a little longer
         p0 = time.perf_counter()
         while time.perf_counter() - p0 < 0.6:
@@ -239,14 +241,13 @@ def run_b200(args, rank, local_rank, world):
 
     assert int(err.item()) == 0, "forbidden decay flagged"
     # the only collective of the path: the tiny weight-statistics allreduce (outside the timed loop)
-    gstats = stats.clone()
     if world > 1:
         mx = gstats[[0, 3]].clone()
         sm = gstats[[1, 2]].clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         gstats = torch.stack([mx[0], sm[0], sm[1], mx[1]])
-    n_acc = float(world) * n * (max(args.warmup, 3) + args.steps)
+    n_acc = float(world) * n * args.steps
     global_stats = {"max_w": float(gstats[0]), "mean_w": float(gstats[1]) / n_acc}
 
     # ---- end to end through the public API with HOST output buffers (D2H inside the timed region)

@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -331,8 +332,12 @@ Nvrtc* load_nvrtc() {
     static bool tried = false;
     if (tried) return n.handle ? &n : nullptr;
     tried = true;
-    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    // The toolkit's own NVRTC first (CUDA 12.9 emits PTX ISA 8.8, needed for 256-bit stores); a process
+    // that already holds an older libnvrtc.so.12 (e.g. the one bundled with torch) is found last.
+    const char* names[] = {getenv("PS_NVRTC_PATH"), "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so",
+                           "libnvrtc.so.12", "libnvrtc.so"};
     for (const char* nm : names) {
+        if (!nm || !*nm) continue;
         n.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
         if (n.handle) break;
     }

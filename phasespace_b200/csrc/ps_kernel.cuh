@@ -105,11 +105,12 @@ struct Ctx {
 
 // ------------------------------------------------------------------ kinematics (kinematics.py)
 // kin.mass, kinematics.py:93-104, metric (-,-,-,+) summed left to right
+// (never FMA-contracted: E^2 - p^2 of a boosted vector cancels, so the last bit of each product matters)
 __device__ __forceinline__ double kin_mass(double x, double y, double z, double e) {
-    double s = -(x * x);
-    s = s + -(y * y);
-    s = s + -(z * z);
-    s = s + e * e;
+    double s = -__dmul_rn(x, x);
+    s = __dadd_rn(s, -__dmul_rn(y, y));
+    s = __dadd_rn(s, -__dmul_rn(z, z));
+    s = __dadd_rn(s, __dmul_rn(e, e));
     return sqrt(s);
 }
 
@@ -339,9 +340,12 @@ __device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long 
     if constexpr (REST) {
         M = prm.mass[0];
     } else if constexpr (PS_EXACT || Node::slot < 0) {
-        M = kin_mass(ppx, ppy, ppz, pe);  // phasespace.py:322
+        M = kin_mass(ppx, ppy, ppz, pe);  // phasespace.py:322: re-derived from the (boosted) 4-vector
     } else {
-        M = c.ms[Node::slot];  // fast: the mass this particle was generated with
+        // fast: the mass this particle was generated with.  Cheaper, and better conditioned than the
+        // reference's E^2 - p^2 of a boosted vector (whose error ~ eps*gamma^2 is amplified near
+        // threshold and can even turn an allowed decay into a "forbidden" one).
+        M = c.ms[Node::slot];
     }
 
     double m[N];
@@ -368,7 +372,8 @@ __device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long 
 #pragma unroll
         for (int j = 0; j < N; ++j) {  // phasespace.py:379-384
             sum_ = sum_ + m[j];
-            inv[j] = r[j] * avail + sum_;
+            // never contracted to an FMA: near threshold (a - b - c) amplifies the last bit of inv[]
+            inv[j] = __dadd_rn(__dmul_rn(r[j], avail), sum_);
         }
     }
 
@@ -504,12 +509,28 @@ __device__ __forceinline__ double node_w_max(const C& c, double M, Seq<J...>) {
 
 // ------------------------------------------------------------------ stores
 // One 256-bit store per particle per thread: a warp writes 32 consecutive 32-byte rows = 1 KiB
-// contiguous, i.e. eight full 128-byte lines per instruction (STG.E.ENL2.256 on sm_100a).
+// contiguous, i.e. eight full 128-byte lines per instruction (STG.E.ENL2.256 on sm_100a; PTX ISA 8.8,
+// CUDA >= 12.9).  Older NVRTC versions (PTX 8.7) fall back to two 128-bit halves.
+#if defined(__CUDACC_VER_MAJOR__) && (__CUDACC_VER_MAJOR__ * 100 + __CUDACC_VER_MINOR__ >= 1209)
+#define PS_HAVE_V4F64 1
+#else
+#define PS_HAVE_V4F64 0
+#endif
 __device__ __forceinline__ void store_row(double* p, double a, double b, double c, double d) {
+#if PS_HAVE_V4F64
     asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#else
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p + 2), "d"(c), "d"(d) : "memory");
+#endif
 }
 __device__ __forceinline__ void load_row(const double* p, double& a, double& b, double& c, double& d) {
+#if PS_HAVE_V4F64
     asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#else
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(d) : "l"(p + 2));
+#endif
 }
 
 template <class C, int... S>
