@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphasespace_b200.so")
+LIB_PATH = os.environ.get("PS_B200_LIB") or os.path.join(_HERE, "libphasespace_b200.so")
 
 PS_MASS_FIXED, PS_MASS_GAUSS, PS_MASS_BW, PS_MASS_RELBW, PS_MASS_USER = range(5)
 PS_GEN_NORMALIZE, PS_GEN_EXACT = 1, 2

@@ -27,7 +27,9 @@
 #include "ps_registry.h"
 #include "ps_samplers.cuh"
 
+#ifndef PS_BLOCK
 #define PS_BLOCK 256
+#endif
 
 namespace {
 
@@ -418,8 +420,10 @@ int get_kernel(const ps_tree* t, int variant, int boost, int dbg, int exact, con
     return rc;
 }
 
-// grid = SM count x resident CTAs per SM (a persistent grid-stride kernel), capped by the tile count
-int pick_grid(const void* fn, long long n_events, int* grid) {
+// Launch shape (see genbod_body): a persistent grid of SM count x resident CTAs with a static tile stride;
+// for trees with at most PS_CHUNKED_MAX_P particles (memory-bound) a covering grid with up to 16
+// consecutive tiles per CTA.
+int pick_grid(const ps_tree* t, const void* fn, long long n_events, int* grid, int* tiles_per_cta) {
     Registry& r = registry();
     int per_sm = 0;
     {
@@ -439,10 +443,19 @@ int pick_grid(const void* fn, long long n_events, int* grid) {
         r.blocks_per_sm[fn] = per_sm;
     }
     const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
-    long long g = (long long)sms * per_sm;
-    if (g > tiles) g = tiles;
-    if (g < 1) g = 1;
-    *grid = (int)g;
+    int k = 0;
+    long long g;
+    if (t->n_particles <= PS_CHUNKED_MAX_P) {  // must match CHUNKED in genbod_body
+        k = 16;
+        while (k > 1 && tiles / k < (long long)sms * per_sm * 4) k >>= 1;  // keep several waves of CTAs
+        while ((tiles + k - 1) / k > 2147483647LL) k <<= 1;
+        g = (tiles + k - 1) / k;
+    } else {
+        g = (long long)sms * per_sm;
+        if (g > tiles) g = tiles;
+    }
+    *grid = (int)(g < 1 ? 1 : g);
+    *tiles_per_cta = k;
     return 0;
 }
 
@@ -477,6 +490,7 @@ int fill_params(const ps_tree* t, PsParams& p, uint64_t seed, uint64_t first_eve
     p.stats = stats;
     p.err_flag = err_flag;
     p.normalize = (flags & PS_GEN_NORMALIZE) ? 1 : 0;
+    p.tiles_per_cta = 0;
     return 0;
 }
 
@@ -489,7 +503,7 @@ int launch_generate(const ps_tree* t, PsParams& p, uint32_t flags, void* stream)
     int rc = get_kernel(t, PS_VARIANT_GENERATE, p.boost_to ? 1 : 0, p.dbg_u ? 1 : 0, (flags & PS_GEN_EXACT) ? 1 : 0, &fn);
     if (rc) return rc;
     int grid = 1;
-    rc = pick_grid(fn, p.n_events, &grid);
+    rc = pick_grid(t, fn, p.n_events, &grid, &p.tiles_per_cta);
     if (rc) return rc;
     void* args[] = {&p};
     PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, 0, (cudaStream_t)stream));
@@ -678,9 +692,11 @@ extern "C" int ps_unweight_mask(const ps_tree* tree, uint64_t seed, uint64_t fir
     const void* fn = nullptr;
     rc = get_kernel(tree, PS_VARIANT_MASK, 0, 0, (flags & PS_GEN_EXACT) ? 1 : 0, &fn);
     if (rc) return rc;
-    int grid = 1;
-    rc = pick_grid(fn, n_events, &grid);
-    if (rc) return rc;
+    int dev = 0, sms = 0;
+    PS_CUDA(cudaGetDevice(&dev));
+    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
+    int grid = (int)((long long)sms * 8 < tiles ? (long long)sms * 8 : tiles);
     void* args[] = {&p, &w_bound, &mask, &tile_counts};
     PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, 0, (cudaStream_t)stream));
     g_launches.fetch_add(1);

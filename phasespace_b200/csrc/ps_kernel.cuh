@@ -22,6 +22,7 @@
 #include "ps_params.h"
 #include "ps_philox.cuh"
 #include "ps_samplers.cuh"
+#include "ps_fastmath.cuh"
 
 #ifndef PS_EXACT
 #define PS_EXACT 0
@@ -30,7 +31,7 @@
 #define PS_BLOCK 256
 #endif
 #ifndef PS_MIN_BLOCKS
-#define PS_MIN_BLOCKS 1
+#define PS_MIN_BLOCKS 2
 #endif
 
 namespace psk {
@@ -248,9 +249,9 @@ __device__ __forceinline__ void genbod_step_fast(C& c, const double* pd, const d
     const double ua = c.template next<AB>();
     const double ub = c.template next<AB + 1>();
     const double cz = 2.0 * ua - 1.0;
-    const double sz = sqrt(fma(-cz, cz, 1.0));
+    const double sz = sqrt_pos(fma(-cz, cz, 1.0));
     double sy, cy;
-    sincospi(2.0 * ub, &sy, &cy);
+    sincos_2pi(ub, sy, cy);
     const double t = sz * pd[K - 1];
     if constexpr (K == 1) {
         // particles 0 and 1 are back to back: (0, +-pd0, 0) rotated
@@ -372,8 +373,13 @@ __device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long 
 #pragma unroll
         for (int j = 0; j < N; ++j) {  // phasespace.py:379-384
             sum_ = sum_ + m[j];
-            // never contracted to an FMA: near threshold (a - b - c) amplifies the last bit of inv[]
-            inv[j] = __dadd_rn(__dmul_rn(r[j], avail), sum_);
+#if PS_EXACT
+            inv[j] = r[j] * avail + sum_;
+#else
+            // r[0] = 0 and r[N-1] = 1 are exact; the middle ones are never contracted to an FMA because
+            // near threshold (a - b - c) amplifies the last bit of inv[]
+            inv[j] = j == 0 ? sum_ : (j == N - 1 ? avail + sum_ : __dadd_rn(__dmul_rn(r[j], avail), sum_));
+#endif
         }
     }
 
@@ -406,9 +412,9 @@ __device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long 
             const double a = inv[j + 1], b = inv[j], cc = m[j + 1];
             const double amb = a - b, apb = a + b;
             const double xx = (amb - cc) * (apb + cc) * (amb + cc) * (apb - cc);
-            ra[j] = 1.0 / a;
+            ra[j] = rcp_pos(a);
             const double hra = 0.5 * ra[j];
-            pd[j] = sqrt(xx) * hra;
+            pd[j] = sqrt_pos(xx) * hra;
             enew[j + 1] = fma(amb, apb, cc * cc) * hra;  // (a^2 + c^2 - b^2) / 2a
             esub[j] = a - enew[j + 1];
         }
@@ -418,9 +424,9 @@ __device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long 
         genbod_steps_fast<N, AB0>(c, pd, ra, enew, esub, x, y, z, e, MakeSeq<N - 1>{});
         if constexpr (!REST) {
             // boost by the parent: u = gamma*beta = p/M, gamma = E/M;  p' = p + (u.p/(gamma+1) + E) u ; E' = gamma E + u.p
-            const double rM = 1.0 / M;
+            const double rM = rcp_pos(M);
             const double ux = ppx * rM, uy = ppy * rM, uz = ppz * rM, g = pe * rM;
-            const double g1 = 1.0 / (g + 1.0);
+            const double g1 = rcp_pos(g + 1.0);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const double up = fma(ux, x[j], fma(uy, y[j], uz * z[j]));
@@ -550,7 +556,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------ the kernel
-// Grid-stride over tiles of PS_BLOCK events; the host launches (SM count x resident CTAs) blocks.
+// Work distribution over tiles of PS_BLOCK events, two shapes (compile-time, by tree size):
+//   P > PS_CHUNKED_MAX_P: persistent grid (SM count x resident CTAs), CTA b takes tiles b, b + grid, b + 2 grid, ...
+//       The per-CTA prologue (Philox round keys, mass constants) and the statistics epilogue are paid
+//       once; best for compute-heavy trees (3 bodies and more).
+//   else: the grid covers all tiles and CTA b takes the K = prm.tiles_per_cta consecutive tiles from b*K.  The hardware
+//       dispatches CTAs in index order, so chip-wide the stores sweep HBM in address order like a
+//       memset (tools/store_bench.cu: 7.3-7.5 TB/s against 6.3 TB/s for the persistent stride, whose
+//       CTAs drift apart); best for memory-bound trees (2 bodies).
 template <class Tree, bool BOOST, bool DBG>
 __device__ __forceinline__ void genbod_body(const PsParams& prm) {
     constexpr int P = Tree::n_below;
@@ -560,7 +573,14 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
     double st_max = 0.0, st_sum = 0.0, st_sum2 = 0.0, st_wmax = 0.0;
     bool bad_any = false;
     const long long n = prm.n_events;
-    for (long long tile = blockIdx.x; tile * PS_BLOCK < n; tile += gridDim.x) {
+    // the shape is a property of the tree (PS_CHUNKED_MAX_P): the host launches accordingly
+    constexpr bool CHUNKED = P <= PS_CHUNKED_MAX_P;
+    const long long n_tiles = (n + PS_BLOCK - 1) / PS_BLOCK;
+    long long tile = CHUNKED ? (long long)blockIdx.x * prm.tiles_per_cta : (long long)blockIdx.x;
+    const long long tile_end = CHUNKED ? (tile + prm.tiles_per_cta < n_tiles ? tile + prm.tiles_per_cta : n_tiles) : n_tiles;
+    const long long tile_step = CHUNKED ? 1 : (long long)gridDim.x;
+    for (; tile < tile_end; tile += tile_step) {
+        {
         const long long i = tile * PS_BLOCK + threadIdx.x;
         if (i < n) {
             Ctx<P, DBG> c;
@@ -599,6 +619,7 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
             st_sum += w_out;
             st_sum2 += w_out * w_out;
             st_wmax = fmax(st_wmax, w_max);
+        }
         }
     }
     if (bad_any) *prm.err_flag = PS_ERR_FORBIDDEN;

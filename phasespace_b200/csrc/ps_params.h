@@ -3,6 +3,8 @@
 #ifndef PS_PARAMS_H_
 #define PS_PARAMS_H_
 
+/* trees with at most this many particles are memory-bound and use the covering (chunked) grid */
+#define PS_CHUNKED_MAX_P 2
 #define PS_MAX_SLOTS 40 /* particles in one decay tree, excluding the top */
 
 /* mass-model kinds (mirrors include/phasespace_b200.h) */
@@ -43,6 +45,7 @@ typedef struct PsParams {
     double* stats;             /* NULL or [max w_out, sum w_out, sum w_out^2, max w_max] */
     int* err_flag;
     int normalize; /* 1: weights = w / w_max ; 0: weights = w and weights_max = w_max */
+    int tiles_per_cta; /* chunked grid only: CTA b takes tiles [b*K, (b+1)*K) */
 } PsParams;
 
 #endif

@@ -10,6 +10,12 @@
 #ifndef PS_PHILOX_CUH_
 #define PS_PHILOX_CUH_
 
+// 1: inline mul.wide.u32; 0: __umulhi + mul (the compiler fuses them into IMAD.WIDE as well and keeps the
+// round keys in uniform registers, which costs fewer vector registers)
+#ifndef PS_PHILOX_ASM
+#define PS_PHILOX_ASM 0
+#endif
+
 namespace psk {
 
 struct Philox2d {
@@ -22,8 +28,15 @@ __device__ __forceinline__ Philox2d philox_pair(unsigned long long seed, unsigne
     unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        // one IMAD.WIDE.U32 per multiplier yields both halves of the 32x32 product
+        unsigned int hi0, lo0, hi1, lo1;
+#if PS_PHILOX_ASM
+        asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(0xD2511F53u));
+        asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(0xCD9E8D57u));
+#else
+        hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#endif
         c0 = hi1 ^ c1 ^ k0;
         c1 = lo1;
         c2 = hi0 ^ c3 ^ k1;
