@@ -1,0 +1,67 @@
+"""Accept-reject unweighting fused with the generator (BASELINE config 5).
+
+The consumer of weighted phase-space events usually unweights them (accept event ``i`` when
+``u_i * w_bound < w_i / w_max``).  Storing every candidate first would cost 8 + 32 P bytes per
+*generated* event; instead
+
+1. ``ps_unweight_mask``   recomputes only the weights (no 4-vectors are formed or stored), draws the
+                          acceptance uniform from Philox stream 1 and emits one bit per event plus a
+                          count per tile of 256 events,
+2. ``ps_unweight_scan`` / ``ps_unweight_index``  turn that into the ordered list of accepted event indices,
+3. ``ps_generate_indexed`` regenerates exactly those events (the RNG is counter based) into a dense slab.
+
+The result is ordered by event index and independent of grid size, chunking and GPU count.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from .phasespace import _device, _ptr
+
+
+def generate_unweighted(decay, n_events: int, seed: int, *, w_bound: float = 1.0, first_event: int = 0,
+                        exact: bool = False):
+    """Unweighted events among the candidates ``[first_event, first_event + n_events)`` of stream ``seed``.
+
+    ``w_bound`` is the acceptance bound on the *normalised* weight ``w / w_max`` (1.0 is always safe; a
+    smaller measured maximum raises the efficiency).  Returns ``(particles, event_index, weights)``:
+    ``particles`` maps names to ``(n_accepted, 4)`` tensors, ``event_index`` the accepted global event
+    indices (int64, ascending) and ``weights`` their normalised weights.
+    """
+    device = _device()
+    n = int(n_events)
+    compiled = decay.compile()
+    if compiled.n_user:
+        raise ValueError("unweighting needs in-kernel mass functions (no arbitrary Python callables)")
+    decay._mark_generate_called()
+    lib = _lib.lib
+    stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    n_tiles = (n + _lib.TILE - 1) // _lib.TILE
+    mask = torch.empty(((n + 31) // 32,), dtype=torch.int32, device=device)
+    counts = torch.empty((max(n_tiles, 1),), dtype=torch.int32, device=device)
+    offsets = torch.empty((max(n_tiles, 1),), dtype=torch.int64, device=device)
+    total = torch.zeros((1,), dtype=torch.int64, device=device)
+    err = torch.zeros((1,), dtype=torch.int32, device=device)
+    flags = _lib.PS_GEN_EXACT if exact else 0
+    seed = int(seed) & (2**64 - 1)
+    if n > 0:
+        _lib.check(lib.ps_unweight_mask(compiled.handle, seed, int(first_event), n, float(w_bound), _ptr(mask),
+                                        _ptr(counts), _ptr(err), flags, stream))
+        _lib.check(lib.ps_unweight_scan(_ptr(counts), n_tiles, _ptr(offsets), _ptr(total), stream))
+    n_acc = int(total.item())
+    if int(err.item()):
+        raise _lib.ForbiddenDecayError("Forbidden decay")
+    index = torch.empty((n_acc,), dtype=torch.int64, device=device)
+    weights = torch.empty((n_acc,), dtype=torch.float64, device=device)
+    slab = torch.empty((compiled.n_particles, n_acc, 4), dtype=torch.float64, device=device)
+    if n_acc > 0:
+        _lib.check(lib.ps_unweight_index(_ptr(mask), _ptr(offsets), int(first_event), n, _ptr(index), stream))
+        _lib.check(lib.ps_generate_indexed(
+            compiled.handle, seed, _ptr(index), n_acc, None, 0, None, _ptr(weights), None, _ptr(slab),
+            int(4 * n_acc), None, _ptr(err), flags | _lib.PS_GEN_NORMALIZE, stream))
+    parts = {name: slab[compiled.slots[name]] for name in compiled.names}
+    return parts, index, weights

@@ -1,0 +1,219 @@
+"""Ports of the reference's generating tests (tests/test_generate.py, tests/test_chain.py:95-114) plus the
+argument semantics of SURVEY.md appendix B, on the GPU."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import phasespace_b200 as phasespace
+from phasespace_b200 import GenParticle
+
+from .helpers import decays as D
+
+pytestmark = pytest.mark.gpu
+B0_MASS, PION_MASS = D.B0_MASS, D.PION_MASS
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def test_one_event():
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    norm_weights, particles = decay.generate(n_events=1)
+    assert norm_weights.shape[0] == 1
+    assert np.all(_np(norm_weights) < 1)
+    assert len(particles) == 3
+    assert all(part.shape == (1, 4) for part in particles.values())
+
+
+@pytest.mark.parametrize("n_events", [5, 523])
+def test_n_events(n_events):
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    norm_weights, particles = decay.generate(n_events=n_events)
+    assert norm_weights.shape[0] == n_events and norm_weights.dtype == torch.float64 and norm_weights.is_cuda
+    assert np.all(_np(norm_weights) < 1)
+    assert len(particles) == 3
+    assert all(part.shape == (n_events, 4) for part in particles.values())
+    assert len(norm_weights) == n_events
+    # n_events as a tensor, like the reference's tf.Variable use (tests/test_physics.py:86-95)
+    w2, _ = decay.generate(torch.tensor(n_events))
+    assert len(w2) == n_events
+
+
+def test_as_vectors():
+    pytest.importorskip("vector")
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    _, particles = decay.generate(n_events=5, as_vectors=True)
+    assert all(np.stack([p.px, p.py, p.pz, p.E], axis=-1).shape == (5, 4) for p in particles.values())
+
+
+def test_deterministic_events():
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    common_seed = 36
+    w1, p1 = decay.generate(n_events=100, seed=common_seed)
+    wg, pg = decay.generate(n_events=100)
+    wr, pr = decay.generate(n_events=100, seed=152)
+    w2, p2 = decay.generate(n_events=100, seed=common_seed)
+    np.testing.assert_allclose(_np(w1), _np(w2))
+    for a, b in zip(p1.values(), p2.values()):
+        np.testing.assert_allclose(_np(a), _np(b))
+    assert not np.allclose(_np(w1), _np(wr))
+    for a, b in zip(p1.values(), pr.values()):
+        assert not np.allclose(_np(a), _np(b))
+    assert not np.allclose(_np(wg), _np(wr))
+    for a, b in zip(pg.values(), pr.values()):
+        assert not np.allclose(_np(a), _np(b))
+    # the global generator advances between calls (docs/usage.rst:203-213)
+    wg2, _ = decay.generate(n_events=100)
+    assert not np.allclose(_np(wg), _np(wg2))
+    # a Generator object is used and advanced
+    rng = phasespace.random.Generator(7)
+    a, _ = decay.generate(50, seed=rng)
+    b, _ = decay.generate(50, seed=rng)
+    both, _ = decay.generate(100, seed=7)
+    assert torch.equal(torch.cat([a, b]), both)
+
+
+def test_kstargamma():
+    decay = D.to_gen(D.kstar_gamma_desc("gauss"))
+    norm_weights, particles = decay.generate(n_events=1000)
+    assert norm_weights.shape[0] == 1000
+    assert np.all(_np(norm_weights) < 1)
+    assert len(particles) == 4
+    assert list(particles.keys()) == ["K*0", "gamma", "K+", "pi-"]
+    assert all(part.shape == (1000, 4) for part in particles.values())
+
+
+def test_k1gamma():
+    decay = D.to_gen(D.k1_gamma_desc())
+    norm_weights, particles = decay.generate(n_events=1000)
+    assert norm_weights.shape[0] == 1000
+    assert np.all(_np(norm_weights) < 1)
+    assert set(particles.keys()) == {"K1+", "K*0", "gamma", "K+", "pi-", "pi+"}
+    assert all(part.shape == (1000, 4) for part in particles.values())
+
+
+def test_set_children_after_generate():
+    top = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 2)
+    top.generate(3)
+    with pytest.raises(RuntimeError):
+        top.set_children(GenParticle("a", 1.0), GenParticle("b", 1.0))
+
+
+def test_boost_to_semantics():
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    n = 64
+    row = np.array([1000.0, -2000.0, 30000.0, np.sqrt(1000.0**2 + 2000.0**2 + 30000.0**2 + B0_MASS**2)])
+    boost = np.tile(row, (n, 1))
+    w_arr, p_arr = decay.generate(n, boost_to=boost, seed=3)
+    w_one, p_one = decay.generate(n, boost_to=row[None, :], seed=3)
+    w_list, p_list = decay.generate(n, boost_to=[list(c) for c in boost.T], seed=3)  # a list is read transposed (ps.py:51-53)
+    w_t, p_t = decay.generate(n, boost_to=torch.as_tensor(boost, device="cuda"), seed=3)
+    for other in (p_one, p_list, p_t):
+        for name in p_arr:
+            assert torch.equal(p_arr[name], other[name])
+    total = sum(_np(v) for v in p_arr.values())
+    np.testing.assert_allclose(total, boost, rtol=1e-12)
+    with pytest.raises(ValueError, match="doesn't match the boost_to input size"):
+        decay.generate(n, boost_to=boost[:5])
+    with pytest.raises(ValueError):
+        decay.generate(n, boost_to=np.ones((n, 3)))
+
+
+def test_normalize_false_returns_three():
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 4)
+    w, wmax, parts = decay.generate(100, normalize_weights=False, seed=1)
+    wn, _ = decay.generate(100, seed=1)
+    np.testing.assert_allclose(_np(w) / _np(wmax), _np(wn), rtol=1e-14)
+    assert torch.all(wmax == wmax[0])
+
+
+def test_empty_and_odd_sizes():
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    w, p = decay.generate(0)
+    assert w.shape == (0,) and all(v.shape == (0, 4) for v in p.values())
+    for n in (1, 31, 33, 255, 257, 100_001):
+        w, p = decay.generate(n, seed=4)
+        assert w.shape == (n,) and torch.isfinite(w).all()
+        assert all(torch.isfinite(v).all() for v in p.values())
+
+
+def test_golden_vectors():
+    """The committed oracle vectors (tests/golden/oracle_vectors.npz) through the CUDA path."""
+    from .golden import make_golden
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_vectors.npz"))
+    for name, (desc, n, boost_seed) in make_golden.CASES.items():
+        gen = D.to_gen(desc)
+        boost = torch.as_tensor(g[f"{name}/boost"]) if boost_seed is not None else None
+        for exact in (True, False):
+            w, wmax, parts = gen.generate(n, boost_to=boost, normalize_weights=False, exact=exact,
+                                          debug_uniforms=torch.as_tensor(g[f"{name}/draws"]))
+            scale = D.B0_MASS if boost is None else float(boost[:, 3].max())
+            ref_w = g[f"{name}/weights"]
+            assert np.max(np.abs(_np(w) - ref_w)) <= 1e-11 * np.max(ref_w), name
+            np.testing.assert_allclose(_np(wmax), g[f"{name}/weights_max"], rtol=1e-11, err_msg=name)
+            got = np.stack([_np(v) for v in parts.values()])
+            assert np.max(np.abs(got - g[f"{name}/particles"])) / scale <= 1e-11, name
+
+
+def test_jit_compiled_tree():
+    """A tree with no ahead-of-time kernel (11 bodies; a 3 -> (2, 3) chain) is specialised by NVRTC."""
+    from oracle import genbod_numpy as orc
+    from oracle.philox import uniform_table
+
+    n = 2000
+    masses = [PION_MASS] * 11
+    desc = D.flat_desc(11, masses=masses)
+    tree = D.to_oracle(desc)
+    ref_w, ref_p = orc.generate(tree, n, uniform_table(8, 0, n, orc.n_draws(tree)))
+    w, p = D.to_gen(desc).generate(n, seed=8)
+    np.testing.assert_allclose(_np(w), ref_w, rtol=1e-11)
+    for name in ref_p:
+        assert np.max(np.abs(_np(p[name]) - ref_p[name])) / B0_MASS <= 1e-12
+    chain = ("B", 5279.58, "fixed", 0.0, [
+        ("X", 1500.0, "relbw", 100.0, [("a", 139.57, "fixed", 0.0, []), ("b", 493.677, "fixed", 0.0, [])]),
+        ("Y", 2000.0, "gauss", 50.0, [("c", 139.57, "fixed", 0.0, []), ("d", 139.57, "fixed", 0.0, []), ("e", 0.0, "fixed", 0.0, [])]),
+        ("f", 105.66, "fixed", 0.0, []),
+    ])
+    tree = D.to_oracle(chain)
+    ref_w, ref_p = orc.generate(tree, n, uniform_table(9, 0, n, orc.n_draws(tree)))
+    w, p = D.to_gen(chain).generate(n, seed=9)
+    assert list(p) == orc.output_names(tree)
+    assert np.max(np.abs(_np(w) - ref_w)) <= 1e-11 * ref_w.max()
+    for name in ref_p:
+        assert np.max(np.abs(_np(p[name]) - ref_p[name])) / B0_MASS <= 5e-12, name
+
+
+def test_generate_host_matches_device():
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    n = 300_007
+    w, p = decay.generate(n, seed=21)
+    hw, hp = decay.generate_host(n, seed=21, chunk_events=65536)
+    assert np.array_equal(_np(w), hw)
+    for name in p:
+        assert np.array_equal(_np(p[name]), hp[name])
+    chain = D.to_gen(D.kstar_gamma_desc("relbw"))
+    w, wmax, p = chain.generate(50_000, seed=2, normalize_weights=False)
+    hw, hwmax, hp = chain.generate_host(50_000, seed=2, normalize_weights=False, chunk_events=8192)
+    assert np.array_equal(_np(w), hw) and np.array_equal(_np(wmax), hwmax)
+    assert all(np.array_equal(_np(p[k]), hp[k]) for k in p)
+
+
+def test_kinematics_helpers():
+    from phasespace_b200 import kinematics as kin
+
+    rng = np.random.default_rng(1)
+    p = rng.normal(0, 1000.0, (1000, 3))
+    vec = np.concatenate([p, np.sqrt((p * p).sum(1, keepdims=True) + 139.57**2)], axis=1)
+    np.testing.assert_allclose(_np(kin.mass(vec))[:, 0], 139.57, rtol=1e-8)
+    b = rng.uniform(-0.5, 0.5, (1000, 3))
+    out = _np(kin.lorentz_boost(vec, b))
+    from oracle import genbod_numpy as orc
+
+    np.testing.assert_allclose(out, orc.lorentz_boost(vec, b), rtol=1e-13, atol=1e-10)
+    same = _np(kin.lorentz_boost(vec, np.zeros((1, 3))))
+    np.testing.assert_array_equal(same, vec)

@@ -1,0 +1,64 @@
+"""GenMultiDecay.generate: the check_norm helper and the generating halves of the reference's
+tests/fromdecay/test_fromdecay.py:14-37, 59-188."""
+
+import numpy as np
+import pytest
+import torch
+
+import phasespace_b200 as phasespace
+from phasespace_b200.fromdecay import GenMultiDecay
+
+from .helpers import decays as D
+from .helpers import example_decay_chains
+
+pytestmark = pytest.mark.gpu
+
+
+def check_norm(full_decay, **kwargs):
+    all_return_args = []
+    for norm in (True, False):
+        return_args = full_decay.generate(normalize_weights=norm, **kwargs)
+        assert len(return_args) == (2 if norm else 3)
+        assert sum(len(w) for w in return_args[0]) == kwargs["n_events"]
+        if not norm:
+            assert all(len(w) == len(mw) for w, mw in zip(return_args[0], return_args[1]))
+        all_return_args.append(return_args)
+    return all_return_args
+
+
+def test_single_chain():
+    container = GenMultiDecay.from_dict(example_decay_chains.dplus_single, tolerance=1e-10)
+    check_norm(container, n_events=1)
+    (_, decay_list), _ = check_norm(container, n_events=100)
+    assert len(decay_list) == 1
+    events = decay_list[0]
+    assert set(events.keys()) == {"K-", "pi+", "pi+ [0]", "pi0", "gamma", "gamma [0]"}
+    assert all(len(p) == 100 for p in events.values())
+
+
+@pytest.mark.parametrize("chain", ["pi0_4branches", "dplus_4grandbranches", "dstarplus_big_decay"])
+def test_branching(chain):
+    tol = None if chain == "dstarplus_big_decay" else 1e-10
+    container = GenMultiDecay.from_dict(getattr(example_decay_chains, chain), tolerance=tol)
+    check_norm(container, n_events=1)
+    check_norm(container, n_events=100)
+    (weights, events), _ = check_norm(container, n_events=20_000, seed=5)
+    assert all(torch.isfinite(w).all() and (w <= 1 + 1e-12).all() for w in weights)
+    assert max(float(w.max()) for w in weights) > 0.0
+
+
+def test_list_container_and_global_max():
+    modes = [(0.7, phasespace.nbody_decay(D.B0_MASS, [D.PION_MASS] * 3)),
+             (0.3, D.to_gen(D.kstar_gamma_desc("gauss")))]
+    multi = GenMultiDecay(modes)
+    n = 50_000
+    weights, max_weights, events = multi.generate(n, normalize_weights=False, seed=3)
+    counts = [len(w) for w in weights]
+    assert sum(counts) == n and abs(counts[0] / n - 0.7) < 0.02
+    normed, events2 = multi.generate(n, normalize_weights=True, seed=3)
+    total_max = max(float(mw.max()) for mw in max_weights)  # genmultidecay.py:192-195
+    for w, wn in zip(weights, normed):
+        np.testing.assert_allclose(wn.cpu().numpy(), w.cpu().numpy() / total_max, rtol=1e-14)
+    assert list(events[1]) == ["K*0", "gamma", "K+", "pi-"]
+    again, _ = multi.generate(n, normalize_weights=True, seed=3)
+    assert all(torch.equal(a, b) for a, b in zip(normed, again))
