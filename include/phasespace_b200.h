@@ -6,7 +6,8 @@
  * cites the reference interface it replaces (paths relative to /root/reference/src/phasespace).
  *
  * Ownership: every device buffer is allocated and owned by the caller; the library keeps no global
- * state beyond immutable ps_tree objects and a cache of compiled kernels.  Calls are asynchronous on
+ * state beyond immutable ps_tree objects, a cache of compiled kernels and (ps_generate_host only) a
+ * per-device staging arena of two chunk buffers.  Calls are asynchronous on
  * the stream passed in (a CUstream / cudaStream_t handle; 0 = default stream) and thread-safe.
  * All functions return 0 on success or a negative PS_E_* code; ps_last_error() (thread local)
  * describes the failure.  4-vectors are [px, py, pz, E] (kinematics.py:32,45), fp64 throughout.

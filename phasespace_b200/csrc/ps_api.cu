@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <mutex>
 #include <string>
@@ -537,6 +538,32 @@ extern "C" int ps_generate_indexed(const ps_tree* tree, uint64_t seed, const int
 }
 
 // ---------------------------------------------------------------------------------- host-buffer path
+namespace {
+
+// Staging arena of the host-buffer path, cached per device: two chunk buffers, two streams and an error
+// flag.  cudaMalloc / cudaFree cost tens of milliseconds per call, as much as generating 1e9 events.
+struct HostArena {
+    std::mutex mu;  // one ps_generate_host at a time per device
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    double* dev[2] = {nullptr, nullptr};
+    size_t capacity = 0;  // doubles per buffer
+    int32_t* d_err = nullptr;
+};
+
+HostArena* host_arena() {
+    static std::mutex mu;
+    static std::map<int, HostArena*> arenas;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    HostArena*& a = arenas[dev];
+    if (!a) a = new HostArena();
+    return a;
+}
+
+}  // namespace
+
 extern "C" int ps_generate_host(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events,
                                 const double* host_boost_to, int64_t boost_rows, double* host_weights,
                                 double* host_weights_max, double* host_particles, int64_t chunk_events, uint32_t flags) {
@@ -546,82 +573,72 @@ extern "C" int ps_generate_host(const ps_tree* tree, uint64_t seed, uint64_t fir
     if (host_boost_to && boost_rows != 1 && boost_rows != n_events)
         return fail(PS_E_INVALID, "The number of events requested (%lld) doesn't match the boost_to input size of (%lld, 4)", (long long)n_events, (long long)boost_rows);
     if (n_events == 0) return 0;
-    if (chunk_events <= 0) chunk_events = 1 << 22;
+    if (chunk_events <= 0) chunk_events = 1 << 23;
     if (chunk_events > n_events) chunk_events = n_events;
     chunk_events = (chunk_events + 7) & ~7LL;
     const int P = tree->n_particles;
     const bool want_wmax = !(flags & PS_GEN_NORMALIZE) && host_weights_max;
     const bool per_event_boost = host_boost_to && boost_rows == n_events && n_events != 1;
-    constexpr int NBUF = 2;
-    cudaStream_t streams[NBUF] = {nullptr, nullptr};
-    double* dev[NBUF] = {nullptr, nullptr};
-    int32_t* d_err = nullptr;
-    // per slot: weights | weights_max | particles(P planes) | boost rows
+    HostArena* arena = host_arena();
+    if (!arena) return fail(PS_E_CUDA, "no CUDA device");
+    std::lock_guard<std::mutex> lock(arena->mu);
+    // per buffer: weights | weights_max | particles (P planes) | boost rows
     const size_t per_slot = (size_t)chunk_events * (size_t)(2 + 4 * P + 4);
-    int rc = 0;
-    auto cleanup = [&]() {
-        for (int b = 0; b < NBUF; ++b) {
-            if (streams[b]) cudaStreamSynchronize(streams[b]);
-            if (dev[b]) cudaFree(dev[b]);
-            if (streams[b]) cudaStreamDestroy(streams[b]);
+    if (!arena->d_err) {
+        PS_CUDA(cudaMalloc(&arena->d_err, sizeof(int32_t)));
+        for (int b = 0; b < 2; ++b) {
+            PS_CUDA(cudaStreamCreateWithFlags(&arena->streams[b], cudaStreamNonBlocking));
+            PS_CUDA(cudaEventCreateWithFlags(&arena->done[b], cudaEventDisableTiming));
         }
-        if (d_err) cudaFree(d_err);
-    };
-#define PS_CUDA_H(expr)                                                                      \
-    do {                                                                                     \
-        cudaError_t err__ = (expr);                                                          \
-        if (err__ != cudaSuccess) {                                                          \
-            rc = fail(PS_E_CUDA, "%s: %s", #expr, cudaGetErrorString(err__));                \
-            cleanup();                                                                       \
-            return rc;                                                                       \
-        }                                                                                    \
-    } while (0)
-    PS_CUDA_H(cudaMalloc(&d_err, sizeof(int32_t)));
-    PS_CUDA_H(cudaMemset(d_err, 0, sizeof(int32_t)));
-    double* d_boost_one = nullptr;
-    for (int b = 0; b < NBUF; ++b) {
-        PS_CUDA_H(cudaStreamCreateWithFlags(&streams[b], cudaStreamNonBlocking));
-        PS_CUDA_H(cudaMalloc(&dev[b], per_slot * sizeof(double)));
     }
+    if (arena->capacity < per_slot) {
+        for (int b = 0; b < 2; ++b) {
+            if (arena->dev[b]) PS_CUDA(cudaFree(arena->dev[b]));
+            arena->dev[b] = nullptr;
+        }
+        arena->capacity = 0;
+        for (int b = 0; b < 2; ++b) PS_CUDA(cudaMalloc(&arena->dev[b], per_slot * sizeof(double)));
+        arena->capacity = per_slot;
+    }
+    cudaStream_t* streams = arena->streams;
+    PS_CUDA(cudaMemsetAsync(arena->d_err, 0, sizeof(int32_t), streams[0]));
+    PS_CUDA(cudaEventRecord(arena->done[1], streams[0]));
+    PS_CUDA(cudaStreamWaitEvent(streams[1], arena->done[1], 0));  // the flag is cleared before either stream writes it
+    int rc = 0;
     int64_t done = 0;
     for (int it = 0; done < n_events; ++it) {
-        const int b = it % NBUF;
+        const int b = it % 2;
         const int64_t n = (n_events - done < chunk_events) ? n_events - done : chunk_events;
-        double* d_w = dev[b];
+        // buffer b was last used two chunks ago: wait (on the host) until its copies have drained
+        if (it >= 2) PS_CUDA(cudaEventSynchronize(arena->done[b]));
+        double* d_w = arena->dev[b];
         double* d_wmax = d_w + chunk_events;
         double* d_p = d_wmax + chunk_events;
         double* d_boost = d_p + (size_t)4 * P * chunk_events;
         const double* boost_arg = nullptr;
         int64_t rows_arg = 0;
         if (host_boost_to) {
-            if (per_event_boost) {
-                PS_CUDA_H(cudaMemcpyAsync(d_boost, host_boost_to + 4 * done, (size_t)n * 32, cudaMemcpyHostToDevice, streams[b]));
-                boost_arg = d_boost;
-                rows_arg = n;
-            } else {
-                PS_CUDA_H(cudaMemcpyAsync(d_boost, host_boost_to, 32, cudaMemcpyHostToDevice, streams[b]));
-                boost_arg = d_boost;
-                rows_arg = 1;
-            }
+            const size_t bytes = per_event_boost ? (size_t)n * 32 : 32;
+            PS_CUDA(cudaMemcpyAsync(d_boost, host_boost_to + (per_event_boost ? 4 * done : 0), bytes, cudaMemcpyHostToDevice, streams[b]));
+            boost_arg = d_boost;
+            rows_arg = per_event_boost ? n : 1;
         }
-        (void)d_boost_one;
         rc = ps_generate(tree, seed, first_event + (uint64_t)done, n, boost_arg, rows_arg, nullptr, nullptr, d_w,
-                         want_wmax ? d_wmax : nullptr, d_p, 4 * chunk_events, nullptr, d_err, flags, streams[b]);
-        if (rc) { cleanup(); return rc; }
-        PS_CUDA_H(cudaMemcpyAsync(host_weights + done, d_w, (size_t)n * 8, cudaMemcpyDeviceToHost, streams[b]));
-        if (want_wmax) PS_CUDA_H(cudaMemcpyAsync(host_weights_max + done, d_wmax, (size_t)n * 8, cudaMemcpyDeviceToHost, streams[b]));
+                         want_wmax ? d_wmax : nullptr, d_p, 4 * chunk_events, nullptr, arena->d_err, flags, streams[b]);
+        if (rc) break;
+        PS_CUDA(cudaMemcpyAsync(host_weights + done, d_w, (size_t)n * 8, cudaMemcpyDeviceToHost, streams[b]));
+        if (want_wmax) PS_CUDA(cudaMemcpyAsync(host_weights_max + done, d_wmax, (size_t)n * 8, cudaMemcpyDeviceToHost, streams[b]));
         for (int s = 0; s < P; ++s)
-            PS_CUDA_H(cudaMemcpyAsync(host_particles + (size_t)s * 4 * n_events + 4 * done, d_p + (size_t)s * 4 * chunk_events,
-                                      (size_t)n * 32, cudaMemcpyDeviceToHost, streams[b]));
+            PS_CUDA(cudaMemcpyAsync(host_particles + (size_t)s * 4 * n_events + 4 * done, d_p + (size_t)s * 4 * chunk_events,
+                                    (size_t)n * 32, cudaMemcpyDeviceToHost, streams[b]));
+        PS_CUDA(cudaEventRecord(arena->done[b], streams[b]));
         done += n;
-        // before reusing the other buffer next iteration, make sure its previous copies are done
-        if (done < n_events) PS_CUDA_H(cudaStreamSynchronize(streams[(it + 1) % NBUF]));
     }
-    for (int b = 0; b < NBUF; ++b) PS_CUDA_H(cudaStreamSynchronize(streams[b]));
     int32_t h_err = 0;
-    PS_CUDA_H(cudaMemcpy(&h_err, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost));
-    cleanup();
-#undef PS_CUDA_H
+    cudaError_t e0 = cudaStreamSynchronize(streams[0]), e1 = cudaStreamSynchronize(streams[1]);
+    if (rc) return rc;
+    if (e0 != cudaSuccess || e1 != cudaSuccess) return fail(PS_E_CUDA, "ps_generate_host: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    PS_CUDA(cudaMemcpy(&h_err, arena->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (h_err) return fail(PS_E_FORBIDDEN, "Forbidden decay");
     return 0;
 }

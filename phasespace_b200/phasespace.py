@@ -385,7 +385,7 @@ class GenParticle:
         return (weights, parts) if normalize_weights else (weights, weights_max, parts)
 
     def generate_host(self, n_events, boost_to=None, normalize_weights: bool = True, seed: SeedLike = None, *,
-                      chunk_events: int = 1 << 22, out: dict | None = None, exact: bool = False):
+                      chunk_events: int = 1 << 23, out: dict | None = None, exact: bool = False):
         """(extension) The same events as :meth:`generate`, delivered into HOST memory.
 
         The events are generated on the device in chunks of ``chunk_events`` and streamed into pinned
