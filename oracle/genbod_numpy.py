@@ -164,7 +164,22 @@ def relbw_cdf(x, m, gamma):
     return c_atan * (np.arctan((x - p) / q) + np.arctan((x + p) / q)) + c_log * np.log((x2r + tpx) / (x2r - tpx))
 
 
-RELBW_NEWTON_ITERS = 6
+RELBW_MAX_ITERS = 8
+
+
+def _relbw_consts(m, gamma):
+    a, b = m * m, m * gamma
+    rho = math.sqrt(a * a + b * b)
+    p, q = math.sqrt(0.5 * (rho + a)), math.sqrt(0.5 * (rho - a))
+    return p, q, 1.0 / (4.0 * rho * q), 1.0 / (8.0 * rho * p)
+
+
+def _relbw_cdf_t(consts, t, x, tt):
+    """``relbw_cdf`` written in the Newton variable: atan((x-p)/q) = t and (x-p)^2 + q^2 = q^2 (1 + tan^2 t)."""
+    p, q, c_atan, c_log = consts
+    big_a = (x + p) * (x + p) + q * q
+    big_b = q * q * (1.0 + tt * tt)
+    return c_atan * (t + np.arctan((x + p) / q)) + c_log * np.log(big_a / big_b)
 
 
 def sample_mass(kind, m, width, lo, hi, u):
@@ -194,20 +209,23 @@ def sample_mass(kind, m, width, lo, hi, u):
         ta, tb = np.arctan((lo - m) / width), np.arctan((hi - m) / width)
         x = m + width * np.tan(ta + u * (tb - ta))
     elif kind == RELBW:
-        a, b = m * m, m * width
-        rho = math.sqrt(a * a + b * b)
-        p, q = math.sqrt(0.5 * (rho + a)), math.sqrt(0.5 * (rho - a))
-        f_lo, f_hi = relbw_cdf(lo, m, width), relbw_cdf(hi, m, width)
-        target = f_lo + u * (f_hi - f_lo)
+        consts = _relbw_consts(m, width)
+        p, q = consts[0], consts[1]
         t_lo, t_hi = np.arctan((lo - p) / q), np.arctan((hi - p) / q)
+        f_lo = _relbw_cdf_t(consts, t_lo, lo, (lo - p) / q)
+        f_hi = _relbw_cdf_t(consts, t_hi, hi, (hi - p) / q)
+        target = f_lo + u * (f_hi - f_lo)
         t = t_lo + u * (t_hi - t_lo)
-        for _ in range(RELBW_NEWTON_ITERS):  # Newton in t = atan((x-p)/q): F is nearly linear in t
+        active = np.ones(np.shape(t), dtype=bool)
+        for _ in range(RELBW_MAX_ITERS):  # Newton in t = atan((x-p)/q): the CDF is nearly linear in t
             tt = np.tan(t)
             x = p + q * tt
-            d = (x * x - a) * (x * x - a) + b * b
-            g = relbw_cdf(x, m, width) - target
-            t = t - g * d / (q * (1.0 + tt * tt))
-            t = np.minimum(np.maximum(t, t_lo), t_hi)
+            g = _relbw_cdf_t(consts, t, x, tt) - target
+            step = g * q * ((x + p) * (x + p) + q * q)
+            t = np.where(active, np.minimum(np.maximum(t - step, t_lo), t_hi), t)
+            active = active & ~(np.abs(step) < 1e-15)
+            if not active.any():
+                break
         x = p + q * np.tan(t)
     else:
         raise ValueError(f"unknown sampler kind {kind}")

@@ -129,7 +129,11 @@ __device__ __forceinline__ double get_w_max(double avail, const double (&m)[N]) 
     for (int i = 1; i < N; ++i) {
         emmin = emmin + m[i - 1];
         emmax = emmax + m[i];
+#if PS_EXACT
         w_max = w_max * pdk(emmax, emmin, m[i]);
+#else
+        w_max = w_max * (sqrt_pos(pdk_x(emmax, emmin, m[i])) * (0.5 * rcp_pos(emmax)));
+#endif
     }
     return w_max;
 }
@@ -607,7 +611,7 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
 #if PS_EXACT
                 w_out = w / w_max;
 #else
-                w_out = WMAX_PER_EVENT ? w / w_max : w * prm.inv_wmax_const;
+                w_out = WMAX_PER_EVENT ? w * rcp_pos(w_max) : w * prm.inv_wmax_const;
 #endif
             } else if (prm.weights_max) {
                 prm.weights_max[i] = w_max;

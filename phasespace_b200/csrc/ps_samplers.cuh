@@ -54,25 +54,33 @@ __device__ __forceinline__ double relbw_cdf(const RelBwConst& k, double x) {
     return k.c_atan * (atan((x - k.p) / k.q) + atan((x + k.p) / k.q)) + k.c_log * log((x2r + tpx) / (x2r - tpx));
 }
 
-#define PS_RELBW_NEWTON_ITERS 6
+#define PS_RELBW_MAX_ITERS 8
 
-// ~ 1/((x^2-m^2)^2 + m^2 w^2) on [lo, hi]; Newton in t = atan((x-p)/q), in which the CDF is
-// nearly linear (its dominant term is t / (4 rho q)).
+// ~ 1/((x^2-m^2)^2 + m^2 w^2) on [lo, hi].  Newton in t = atan((x-p)/q), in which the CDF is nearly linear
+// (its dominant term is t / (4 rho q)).  With x = p + q tan t the first arctangent of the CDF is t itself,
+// (x-p)^2 + q^2 = q^2 sec^2 t, and the Newton step  g * D(x) / (q sec^2 t)  collapses to  g * q * A  with
+// A = (x+p)^2 + q^2: one tan, one atan, one log per iteration.  Stops when the step is below 1e-15 rad
+// (quadratic convergence: typically 3 iterations) or after PS_RELBW_MAX_ITERS.
+__device__ __forceinline__ double relbw_cdf_t(const RelBwConst& k, double t, double x, double tt) {
+    const double A = (x + k.p) * (x + k.p) + k.q * k.q;
+    const double B = k.q * k.q * (1.0 + tt * tt);
+    return k.c_atan * (t + atan((x + k.p) / k.q)) + k.c_log * log(A / B);
+}
 __device__ __forceinline__ double sample_relbw(double m, double w, double lo, double hi, double u) {
     const RelBwConst k = relbw_const(m, w);
-    const double f_lo = relbw_cdf(k, lo), f_hi = relbw_cdf(k, hi);
-    const double target = f_lo + u * (f_hi - f_lo);
     const double t_lo = atan((lo - k.p) / k.q), t_hi = atan((hi - k.p) / k.q);
+    const double f_lo = relbw_cdf_t(k, t_lo, lo, (lo - k.p) / k.q), f_hi = relbw_cdf_t(k, t_hi, hi, (hi - k.p) / k.q);
+    const double target = f_lo + u * (f_hi - f_lo);
     double t = t_lo + u * (t_hi - t_lo);
 #pragma unroll 1
-    for (int it = 0; it < PS_RELBW_NEWTON_ITERS; ++it) {
+    for (int it = 0; it < PS_RELBW_MAX_ITERS; ++it) {
         const double tt = tan(t);
         const double x = k.p + k.q * tt;
-        const double xa = x * x - k.a;
-        const double d = xa * xa + k.b * k.b;
-        const double g = relbw_cdf(k, x) - target;
-        t = t - g * d / (k.q * (1.0 + tt * tt));
-        t = fmin(fmax(t, t_lo), t_hi);
+        const double g = relbw_cdf_t(k, t, x, tt) - target;
+        const double A = (x + k.p) * (x + k.p) + k.q * k.q;
+        const double step = g * k.q * A;
+        t = fmin(fmax(t - step, t_lo), t_hi);
+        if (fabs(step) < 1e-15) break;
     }
     return clamp_mass(k.p + k.q * tan(t), lo, hi);
 }

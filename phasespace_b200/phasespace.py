@@ -88,6 +88,7 @@ class CompiledDecay:
         self.names = sorted(self.slots, key=self.slots.get)
         self.user_columns = {i: lib.ps_tree_user_column(handle, i) for i in range(len(descs))}
         self.has_resonances = any(d[1] != _lib.PS_MASS_FIXED for d in descs)
+        self._err_flags = {}
         self._static_forbidden = self._check_static()
 
     def __del__(self):
@@ -158,19 +159,30 @@ class CompiledDecay:
         device = _device()
         n = int(n_events)
         out = out or {}
-        weights = out.get("weights")
-        if weights is None:
-            weights = torch.empty((n,), dtype=torch.float64, device=device)
-        particles = out.get("particles")
-        if particles is None:
-            particles = torch.empty((self.n_particles, n, 4), dtype=torch.float64, device=device)
-        weights_max = None
-        if not normalize_weights:
-            weights_max = out.get("weights_max")
-            if weights_max is None:
+        weights, particles = out.get("weights"), out.get("particles")
+        weights_max = out.get("weights_max") if not normalize_weights else None
+        if weights is None and particles is None and weights_max is None:
+            # one allocation for everything: [particles (P,n,4) | weights (n) | weights_max (n)]
+            extra = 1 if normalize_weights else 2
+            buf = torch.empty(((4 * self.n_particles + extra) * n,), dtype=torch.float64, device=device)
+            particles = buf[: 4 * self.n_particles * n].view(self.n_particles, n, 4)
+            weights = buf[4 * self.n_particles * n: (4 * self.n_particles + 1) * n]
+            if not normalize_weights:
+                weights_max = buf[(4 * self.n_particles + 1) * n:]
+        else:
+            if weights is None:
+                weights = torch.empty((n,), dtype=torch.float64, device=device)
+            if particles is None:
+                particles = torch.empty((self.n_particles, n, 4), dtype=torch.float64, device=device)
+            if not normalize_weights and weights_max is None:
                 weights_max = torch.empty((n,), dtype=torch.float64, device=device)
         if err is None:
-            err = torch.zeros((1,), dtype=torch.int32, device=device)
+            # trees that cannot fail per event never read the flag back: share one per device
+            err = self._err_flags.get(device)
+            if err is None or self.has_resonances or boost_to is not None:
+                err = torch.zeros((1,), dtype=torch.int32, device=device)
+                if not self.has_resonances:
+                    self._err_flags.setdefault(device, err)
         boost_rows = 0
         if boost_to is not None:
             boost_rows = int(boost_to.shape[0])
