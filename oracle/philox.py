@@ -15,10 +15,10 @@ tests/test_oracle_philox.py.
 Stream layout shared with the kernel (phasespace_b200/csrc/ps_philox.cuh):
 
     key     = (seed & 0xffffffff, seed >> 32)
-    counter = (event & 0xffffffff, event >> 32, column // 2, stream)
-    out[0..3] = philox4x32_10(counter, key)
-    uniform(column) = (((out[2k+1] << 32) | out[2k]) >> 12) * 2**-52   with k = column % 2
-    (52-bit mantissa fill of [1,2) minus 1, the same resolution TensorFlow's fp64 uniform has)
+    counter = (event & 0xffffffff, event >> 32, block, stream)
+    the 128-bit outputs of blocks 0, 1, 2, ... of one event form a bit string (word j of block b holds bits
+    128 b + 32 j ... + 31, least significant first); uniform(column) = the 51-bit field at bit offset
+    51 * column, times 2**-51.  (Dense packing: the three-body decay's 5 uniforms need two blocks, not three.)
 
 ``column`` is the index of the draw in the tree-wide draw order, so a
 ``(n_events, n_draws)`` table built here is exactly what the kernel consumes internally.
@@ -61,21 +61,28 @@ def philox4x32_10(counter, key):
     return [c0, c1, c2, c3]
 
 
+UNIFORM_BITS = 51
+
+
 def uniform_table(seed: int, first_event: int, n_events: int, n_columns: int, stream: int = 0):
     """The ``(n_events, n_columns)`` fp64 table of U[0,1) draws the kernel uses for these events."""
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     events = np.arange(first_event, first_event + n_events, dtype=np.uint64)
     out = np.empty((n_events, n_columns), dtype=np.float64)
-    n_blocks = (n_columns + 1) // 2
+    n_blocks = (UNIFORM_BITS * n_columns + 127) // 128
+    words = []  # 32-bit words of the per-event bit string, least significant first
     for blk in range(n_blocks):
-        r = philox4x32_10(
+        words.extend(philox4x32_10(
             (events & _MASK32, events >> _SHIFT32, np.uint64(blk), np.uint64(stream)),
             (np.uint64(seed & 0xFFFFFFFF), np.uint64(seed >> 32)),
-        )
-        for k in range(2):
-            col = 2 * blk + k
-            if col >= n_columns:
-                break
-            bits = ((r[2 * k + 1] << _SHIFT32) | r[2 * k]) >> np.uint64(12)
-            out[:, col] = bits.astype(np.float64) * 2.0**-52
+        ))
+    words.extend([np.zeros(n_events, dtype=np.uint64)] * 2)
+    mask = np.uint64((1 << UNIFORM_BITS) - 1)
+    for col in range(n_columns):
+        i, sh = divmod(UNIFORM_BITS * col, 32)
+        lo = words[i] | (words[i + 1] << _SHIFT32)  # bits 32 i ... 32 i + 63
+        field = lo >> np.uint64(sh)
+        if sh + UNIFORM_BITS > 64:
+            field = field | (words[i + 2] << np.uint64(64 - sh))
+        out[:, col] = (field & mask).astype(np.float64) * 2.0**-UNIFORM_BITS
     return out

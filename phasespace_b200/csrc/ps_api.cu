@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(PS_BLOCK) sample_mass_kernel(int kind, double 
                                                                const double* hi, long long n, unsigned long long seed,
                                                                unsigned long long first_event, double* out) {
     for (long long i = (long long)blockIdx.x * PS_BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * PS_BLOCK) {
-        const double u = psk::philox_pair(seed, first_event + (unsigned long long)i, 0u, 2u).d0;
+        const double u = psk::philox_uniform0(seed, first_event + (unsigned long long)i, 2u);
         out[i] = psk::sample_mass(kind, mass, width, lo[i], hi[i], u);
     }
 }

@@ -85,21 +85,34 @@ struct Ctx {
     double px[P], py[P], pz[P], en[P], ms[P];
     unsigned long long seed, event;
     const double* dbg_row;
-    double stash;
+    unsigned int w[4];  // Philox block currently being consumed
     bool bad;
 
-    // Draw number COL of this event.  Draws are consumed strictly in column order, so the second
-    // double of each Philox block is simply carried in a register until the next (odd) column.
+    // Draw number COL of this event: the 51-bit field at bit offset 51*COL of the event's Philox bit string
+    // (ps_philox.cuh).  Draws are consumed strictly in column order, so at most the block that holds the
+    // first bit and the one that holds the last bit are needed; which blocks are fresh is known at compile time.
     template <int COL>
     __device__ __forceinline__ double next() {
         if constexpr (DBG) {
             return dbg_row[COL];
-        } else if constexpr (COL % 2 == 0) {
-            const Philox2d r = philox_pair(seed, event, COL / 2, 0u);
-            stash = r.d1;
-            return r.d0;
         } else {
-            return stash;
+            constexpr int bit0 = PS_UNIFORM_BITS * COL;
+            constexpr int FB = bit0 / 128, LB = (bit0 + PS_UNIFORM_BITS - 1) / 128;
+            constexpr int PREV = COL == 0 ? -1 : (bit0 - 1) / 128;  // last block touched by the previous column
+            if constexpr (FB > PREV) {
+                const Philox4 r = philox4x32_10(seed, event, FB, 0u);
+                w[0] = r.w[0], w[1] = r.w[1], w[2] = r.w[2], w[3] = r.w[3];
+            }
+            unsigned int x[8] = {w[0], w[1], w[2], w[3], 0u, 0u, 0u, 0u};
+            if constexpr (LB > FB) {
+                const Philox4 r = philox4x32_10(seed, event, LB, 0u);
+                x[4] = r.w[0], x[5] = r.w[1], x[6] = r.w[2], x[7] = r.w[3];
+                w[0] = r.w[0], w[1] = r.w[1], w[2] = r.w[2], w[3] = r.w[3];
+            }
+            constexpr int o = bit0 - 128 * FB, i = o / 32, sh = o % 32;
+            const unsigned int lo = sh ? __funnelshift_r(x[i], x[i + 1], sh) : x[i];
+            const unsigned int hi = sh ? __funnelshift_r(x[i + 1], x[i + 2], sh) : x[i + 1];
+            return uniform_from_bits(lo, hi);
         }
     }
 };
@@ -591,7 +604,6 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
             c.seed = prm.seed;
             c.event = prm.event_index ? (unsigned long long)prm.event_index[i] : prm.first_event + (unsigned long long)i;
             c.dbg_row = DBG ? prm.dbg_u + i * prm.dbg_ncols : nullptr;
-            c.stash = 0.0;
             c.bad = false;
             double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
             if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
@@ -687,7 +699,6 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
             c.seed = prm.seed;
             c.event = prm.first_event + (unsigned long long)i;
             c.dbg_row = nullptr;
-            c.stash = 0.0;
             c.bad = false;
             double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
             if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
@@ -702,7 +713,7 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
             } else {
                 w_max = prm.wmax_const;
             }
-            const double u = philox_pair(prm.seed, c.event, 0u, 1u).d0;
+            const double u = philox_uniform0(prm.seed, c.event, 1u);
             accept = u * w_bound * w_max < w;
             bad_any |= c.bad;
         }

@@ -1,12 +1,14 @@
 // Philox4x32-10 counter-based RNG (Salmon et al., SC'11), keyed on (seed, event index).
 //
 // Replaces the reference's tf.random.Generator (random.py:14-40; draw sites phasespace.py:367,
-// 444-446, 451).  One call yields two fp64 uniforms.  Stream layout (must match oracle/philox.py):
-//   key = (seed_lo, seed_hi); counter = (event_lo, event_hi, column/2, stream)
-//   uniform(column) = ((out[2k+1] << 32 | out[2k]) >> 12) * 2^-52,  k = column % 2
-//   (built as the 52-bit mantissa of a double in [1,2) minus 1: one shift/or and one DADD)
-// so a draw is a pure function of (seed, global event index, column): any sharding of the event
-// range over GPUs, launches or tiles gives bit-identical events.
+// 444-446, 451).  Stream layout (must match oracle/philox.py):
+//   key = (seed_lo, seed_hi); counter = (event_lo, event_hi, block, stream)
+//   the 128-bit outputs of blocks 0, 1, 2, ... of one event form a bit string (word j of block b holds
+//   bits 128 b + 32 j ... + 31, least significant first); uniform number `column` is the 51-bit field at
+//   bit offset 51 * column, scaled by 2^-51.
+// Dense 51-bit packing matters: the headline three-body decay needs 5 uniforms = 255 bits = two Philox
+// blocks instead of three.  A draw is a pure function of (seed, global event index, column): any sharding
+// of the event range over GPUs, launches or tiles gives bit-identical events.
 #ifndef PS_PHILOX_CUH_
 #define PS_PHILOX_CUH_
 
@@ -16,14 +18,16 @@
 #define PS_PHILOX_ASM 0
 #endif
 
+#define PS_UNIFORM_BITS 51
+
 namespace psk {
 
-struct Philox2d {
-    double d0, d1;
+struct Philox4 {
+    unsigned int w[4];
 };
 
-__device__ __forceinline__ Philox2d philox_pair(unsigned long long seed, unsigned long long event,
-                                               unsigned int block, unsigned int stream) {
+__device__ __forceinline__ Philox4 philox4x32_10(unsigned long long seed, unsigned long long event, unsigned int block,
+                                                 unsigned int stream) {
     unsigned int c0 = (unsigned int)event, c1 = (unsigned int)(event >> 32), c2 = block, c3 = stream;
     unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
 #pragma unroll
@@ -44,10 +48,24 @@ __device__ __forceinline__ Philox2d philox_pair(unsigned long long seed, unsigne
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
-    Philox2d out;
-    out.d0 = __hiloint2double((int)(0x3FF00000u | (c1 >> 12)), (int)((c1 << 20) | (c0 >> 12))) - 1.0;
-    out.d1 = __hiloint2double((int)(0x3FF00000u | (c3 >> 12)), (int)((c3 << 20) | (c2 >> 12))) - 1.0;
+    Philox4 out;
+    out.w[0] = c0;
+    out.w[1] = c1;
+    out.w[2] = c2;
+    out.w[3] = c3;
     return out;
+}
+
+// 51 random bits (lo: 32, hi: low 19 bits used) -> U[0,1) with resolution 2^-51: the field fills the low
+// 51 mantissa bits of a double in [1, 1.5), and 2 d - 2 is exact.
+__device__ __forceinline__ double uniform_from_bits(unsigned int lo, unsigned int hi) {
+    return fma(__hiloint2double((int)((hi & 0x7FFFFu) | 0x3FF00000u), (int)lo), 2.0, -2.0);
+}
+
+// first uniform of block 0 of a stream (acceptance draws, stand-alone samplers)
+__device__ __forceinline__ double philox_uniform0(unsigned long long seed, unsigned long long event, unsigned int stream) {
+    const Philox4 r = philox4x32_10(seed, event, 0u, stream);
+    return uniform_from_bits(r.w[0], r.w[1]);
 }
 
 }  // namespace psk

@@ -104,12 +104,13 @@ def _fonll_like_boost(n, mass, seed=1234):
 @pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
 def test_boost_to_per_event(exact):
     boost = _fonll_like_boost(N, D.B0_MASS)
-    # flat tree: weights depend on the boost only through kin.mass(boost_to), identical in oracle and kernel
-    _compare(D.flat_desc(4), N, exact=exact, use_rng=False, boost=boost, tol=1e-11)
+    gamma2 = float(np.max(boost[:, 3]) / D.B0_MASS) ** 2
+    # flat tree: weights depend on the boost only through kin.mass(boost_to), identical in oracle and kernel;
+    # the boosted vectors carry the rounding of gamma ~ E/M (compared on the scale of the largest energy)
+    _compare(D.flat_desc(4), N, exact=exact, use_rng=False, boost=boost, tol=1e-12 * np.sqrt(gamma2) / 10)
     # chain: the reference re-derives each resonance mass as sqrt(E^2 - p^2) of its *boosted* 4-vector
     # (phasespace.py:322 via 564), an expression whose rounding error grows like eps * gamma^2; oracle and
     # kernel only share that noise up to the last bits of sin/cos, so the weights agree to ~1e-12 * gamma^2.
-    gamma2 = float(np.max(boost[:, 3]) / D.B0_MASS) ** 2
     tol_w = 1e-12 * gamma2
     gen, tree = D.to_gen(D.kstar_gamma_desc("gauss")), D.to_oracle(D.kstar_gamma_desc("gauss"))
     draws = uniform_table(5, 0, N, orc.n_draws(tree))
