@@ -165,6 +165,7 @@ def relbw_cdf(x, m, gamma):
 
 
 RELBW_MAX_ITERS = 8
+RELBW_LAST_STEP = 1e-7
 
 
 def _relbw_consts(m, gamma):
@@ -223,7 +224,7 @@ def sample_mass(kind, m, width, lo, hi, u):
             g = _relbw_cdf_t(consts, t, x, tt) - target
             step = g * q * ((x + p) * (x + p) + q * q)
             t = np.where(active, np.minimum(np.maximum(t - step, t_lo), t_hi), t)
-            active = active & ~(np.abs(step) < 1e-15)
+            active = active & ~(np.abs(step) < RELBW_LAST_STEP)  # the error left after a step s is ~0.03 s^2
             if not active.any():
                 break
         x = p + q * np.tan(t)

@@ -4,7 +4,9 @@
 #define PS_PARAMS_H_
 
 /* trees with at most this many particles are memory-bound and use the covering (chunked) grid */
+#ifndef PS_CHUNKED_MAX_P
 #define PS_CHUNKED_MAX_P 2
+#endif
 #define PS_MAX_SLOTS 40 /* particles in one decay tree, excluding the top */
 
 /* mass-model kinds (mirrors include/phasespace_b200.h) */

@@ -17,6 +17,7 @@ from .mass_functions import DEFAULT_CONVERTER
 class GenMultiDecay:
     MASS_WIDTH_TOLERANCE = 0.01
     DEFAULT_MASS_FUNC = "relbw"
+    MAX_STREAMS = 8  # CUDA streams the per-mode kernels are spread over
 
     def __init__(self, gen_particles: list[tuple[float, GenParticle]]):
         """A ``GenParticle``-type container that can handle multiple decays (genmultidecay.py:18-26).
@@ -25,6 +26,15 @@ class GenMultiDecay:
             gen_particles: ``[(probability, GenParticle), ...]``.
         """
         self.gen_particles = gen_particles
+        self._streams = {}
+
+    def _stream_pool(self, n):
+        """Side streams are kept per device: the caching allocator reuses blocks per stream, so fresh streams
+        on every call would turn every output allocation into a cudaMalloc."""
+        pool = self._streams.setdefault(torch.cuda.current_device(), [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream())
+        return pool[:n]
 
     @classmethod
     def from_dict(cls, dec_dict: dict, mass_converter: dict[str, Callable] = None, tolerance: float = None,
@@ -70,13 +80,32 @@ class GenMultiDecay:
         split_rng = np.random.Generator(np.random.Philox(key=rng.seed ^ 0x5DEECE66D, counter=rng.reserve(1)))
         counts = split_rng.multinomial(n_events, probs)
         weights, max_weights, events = [], [], []
-        for (_, gen), n in zip(self.gen_particles, counts):
-            if n == 0:
-                continue
-            weight, max_weight, four_vectors = gen.generate(int(n), normalize_weights=False, seed=rng, **kwargs)
-            weights.append(weight)
-            max_weights.append(max_weight)
-            events.append(four_vectors)
+        # one kernel per populated mode, fanned out over a few CUDA streams; forbidden-decay flags are
+        # collected and checked with a single synchronisation at the end
+        main = torch.cuda.current_stream()
+        populated = [(gen, int(n)) for (_, gen), n in zip(self.gen_particles, counts) if n > 0]
+        n_streams = min(len(populated), self.MAX_STREAMS)
+        streams = self._stream_pool(n_streams) if n_streams > 1 else []
+        for st in streams:
+            st.wait_stream(main)
+        checks = []
+        for k, (gen, n) in enumerate(populated):
+            if streams:
+                with torch.cuda.stream(streams[k % n_streams]):
+                    out = gen.generate(n, normalize_weights=False, seed=rng, _deferred_checks=checks, **kwargs)
+                for t in (out[0], out[1], next(iter(out[2].values()))):
+                    t.record_stream(main)  # the slab was allocated on the side stream and is consumed on `main`
+            else:
+                out = gen.generate(n, normalize_weights=False, seed=rng, _deferred_checks=checks, **kwargs)
+            weights.append(out[0])
+            max_weights.append(out[1])
+            events.append(out[2])
+        for st in streams:
+            main.wait_stream(st)
+        if checks and bool(torch.stack(checks).any().item()):
+            from ..phasespace import ForbiddenDecayError
+
+            raise ForbiddenDecayError("Forbidden decay")
         if normalize_weights:
             total_max = torch.stack([mw.max() for mw in max_weights]).max()  # genmultidecay.py:193
             return [w / total_max for w in weights], events

@@ -326,6 +326,7 @@ class GenParticle:
         as_vectors: bool | None = None,
         exact: bool = False,
         debug_uniforms=None,
+        _deferred_checks: list | None = None,
     ):
         """Generate normalized n-body phase space (reference: ps.py:628-717).
 
@@ -389,8 +390,11 @@ class GenParticle:
             n_events, rng.seed, first_event, boost_to=boost_to, normalize_weights=normalize_weights, exact=exact,
             debug_uniforms=debug_uniforms, user_masses=user_masses,
         )
-        if (compiled.has_resonances or boost_to is not None) and n_events > 0 and int(err.item()):
-            raise ForbiddenDecayError("Forbidden decay")  # ps.py:357-363
+        if (compiled.has_resonances or boost_to is not None) and n_events > 0:
+            if _deferred_checks is not None:  # GenMultiDecay checks all modes with one synchronisation
+                _deferred_checks.append(err)
+            elif int(err.item()):
+                raise ForbiddenDecayError("Forbidden decay")  # ps.py:357-363
         parts = {name: slab[compiled.slots[name]] for name in compiled.names}
         if as_vectors:
             parts = to_vectors(parts)
