@@ -3,18 +3,22 @@
 TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import this module.  The product path (phasespace_b200) never does.
 
-PARITY STATUS: *parity unpinned against a live reference.*  The reference
-(/root/reference/src/phasespace) needs TensorFlow >= 2.19 + tensorflow_probability, neither
-of which is installed or installable here, and its tests hold no numeric golden vectors for
-this path.  This file therefore restates the reference op by op
-(``tnp`` is numpy-API compatible, so the restatement is mechanical: same operations, same
-association order, fp64, no FMA) and is pinned by
-  * the closed-form two-body known answer printed in the reference's README
-    (README.rst:156-176, E(K*)=2715.78804872, E(gamma)=2563.79195128),
-  * the invariants the reference's own tests assert (shapes, w/w_max < 1, key order), and
+PARITY STATUS: the reference itself (/root/reference/src/phasespace) cannot be imported here -- it
+needs TensorFlow >= 2.19 + tensorflow_probability, neither installed nor installable offline -- and
+its tests hold no numeric golden vectors for this path.  This file restates
+the reference op by op (``tnp`` is numpy-API compatible, so the restatement is mechanical: same
+operations, same association order, fp64, no FMA) and is PINNED by
+  * the six events printed in the reference's README (README.rst:156-183), which are real outputs of
+    ``generate()`` for B0 -> K*(-> K+ pi-) gamma: tests/test_oracle.py recovers the four draws of each
+    event from the printed K* and K+ vectors, feeds them to this oracle and gets all four printed
+    4-vectors back to the printed precision (tests/golden/readme_kstargamma.json),
+  * the closed-form two-body energies of the same README block (E(K*)=2715.78804872, E(gamma)=2563.79195128),
+  * the invariants the reference's own tests assert (shapes, w/w_max < 1, key order, error types),
   * 4-momentum conservation / on-shell masses, which hold by construction of the algorithm,
-  * an independent scalar C implementation (oracle/genbod_ref.c) of the same published
-    GENBOD algorithm (F. James, CERN 68-15) it must agree with statistically.
+  * an independent scalar C implementation (oracle/genbod_ref.c) of the same published GENBOD
+    algorithm (F. James, CERN 68-15), through the reference's own KS procedure.
+What stays UNPINNED is the arithmetic the reference delegates to third parties: the TensorFlow Philox
+stream and the tfp / zfit / zfit_physics mass samplers (upstream tests check their shapes only).
 
 Every function cites the reference lines it follows ("ps.py" = src/phasespace/phasespace.py,
 "kin.py" = src/phasespace/kinematics.py).  Random numbers are an *argument* (a

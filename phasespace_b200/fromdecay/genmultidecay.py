@@ -112,86 +112,96 @@ class GenMultiDecay:
         return weights, max_weights, events
 
 
-def _unique_name(name: str, preexisting_particles: set[str]) -> str:
-    """A name not in ``preexisting_particles``: ``name`` or ``"name [i]"`` (genmultidecay.py:200-221)."""
-    if name not in preexisting_particles:
-        preexisting_particles.add(name)
+class _Namer:
+    """Hands out particle names that are unique inside one ``from_dict`` call: the first use of ``"pi+"`` keeps
+    its name, later ones become ``"pi+ [0]"``, ``"pi+ [1]"``, ... (genmultidecay.py:200-221)."""
+
+    def __init__(self):
+        self.taken: set[str] = set()
+
+    def __call__(self, base: str) -> str:
+        name, k = base, 0
+        while name in self.taken:
+            name = f"{base} [{k}]"
+            k += 1
+        self.taken.add(name)
         return name
-    name += " [0]"
-    i = 1
-    while name in preexisting_particles:
-        name = name[: name.rfind("[")] + f"[{str(i)}]"
-        i += 1
-    preexisting_particles.add(name)
-    return name
 
 
-def _get_particle_mass(name: str, mass_converter: dict[str, Callable], mass_func: str, tolerance: float):
-    """Fixed mass if the width is below ``tolerance``, else a mass function (genmultidecay.py:224-249)."""
-    particle = pdg.lookup(name)
-    if particle.width <= tolerance:
-        return float(particle.mass)
-    return mass_converter[mass_func](mass=particle.mass, width=particle.width)
+def _unique_name(name: str, preexisting_particles: set[str]) -> str:
+    """Functional form of :class:`_Namer` over a caller-owned set (same contract as the reference helper)."""
+    namer = _Namer()
+    namer.taken = preexisting_particles
+    return namer(name)
+
+
+def _resonance_mass(evtgen_name: str, model: str, converters: dict[str, Callable], tolerance: float):
+    """Mass of a decaying particle: the PDG mass if its width is at most ``tolerance``, otherwise the mass
+    function ``converters[model](mass, width)`` (genmultidecay.py:224-249)."""
+    entry = pdg.lookup(evtgen_name)
+    if entry.width <= tolerance:
+        return float(entry.mass)
+    return converters[model](mass=entry.mass, width=entry.width)
+
+
+def _model_for(mode: dict, evtgen_name: str, particle_model_map: dict[str, str]) -> str:
+    """Precedence of mass-function names: the mode's own ``zfit`` key, then ``particle_model_map``, then the
+    class default (genmultidecay.py:321-326)."""
+    if "zfit" in mode:
+        return mode["zfit"]
+    return particle_model_map.get(evtgen_name, GenMultiDecay.DEFAULT_MASS_FUNC)
+
+
+def _expand(chain: dict, converters: dict[str, Callable], particle_model_map: dict[str, str], tolerance: float,
+            namer: _Namer, is_top: bool) -> list[tuple[float, GenParticle]]:
+    """Every way ``chain`` (one mother with its list of decay modes) can decay, as ``(probability, GenParticle)``.
+
+    A final-state entry is either a stable particle name or a nested chain with alternatives of its own; the
+    alternatives of all daughters are combined by Cartesian product, probabilities multiplied
+    (genmultidecay.py:252-340)."""
+    (mother,) = chain.keys()
+    mother_name = namer(mother)
+    out = []
+    for mode in chain[mother]:
+        alternatives = []  # per daughter: [(probability, template GenParticle), ...]
+        for daughter in mode["fs"]:
+            if isinstance(daughter, str):
+                alternatives.append([(1.0, GenParticle(namer(daughter), float(pdg.lookup(daughter).mass)))])
+            elif isinstance(daughter, dict):
+                alternatives.append(_expand(daughter, converters, particle_model_map, tolerance, namer, is_top=False))
+            else:
+                raise TypeError(
+                    'Expected elements in decaychain["fs"] to only be str or dict '
+                    f"but found an instance of type {type(daughter)}"
+                )
+        for combo in itertools.product(*alternatives):
+            prob = float(mode["bf"])
+            for daughter_prob, _ in combo:
+                prob *= float(daughter_prob)
+            if is_top:
+                mass = float(pdg.lookup(mother).mass)
+            else:
+                mass = _resonance_mass(mother, _model_for(mode, mother, particle_model_map), converters, tolerance)
+            decay = GenParticle(mother_name, mass).set_children(*(_clone(template) for _, template in combo))
+            out.append((prob, decay))
+    return out
 
 
 def _recursively_traverse(decaychain: dict, mass_converter: dict[str, Callable], particle_model_map: dict[str, str],
                           tolerance: float, preexisting_particles: set[str] = None) -> list[tuple[float, GenParticle]]:
-    """All possible GenParticles of a DecayLanguage dict, one per combination of sub-modes, with the
-    product of their branching fractions (genmultidecay.py:252-340)."""
+    """Entry point kept under the reference's name."""
     if tolerance is None:
         tolerance = GenMultiDecay.MASS_WIDTH_TOLERANCE
-    (original_mother_name,) = decaychain.keys()
-    if preexisting_particles is None:
-        preexisting_particles = set()
-        is_top_particle = True
-    else:
-        is_top_particle = False
-    decay_modes = decaychain[original_mother_name]
-    mother_name = _unique_name(original_mother_name, preexisting_particles)
-    all_decays = []
-    for dm in decay_modes:
-        dm_probability = dm["bf"]
-        daughter_gens = []
-        for daughter_name in dm["fs"]:
-            if isinstance(daughter_name, str):  # stable particles always get a constant mass
-                daughter = GenParticle(
-                    _unique_name(daughter_name, preexisting_particles), float(pdg.lookup(daughter_name).mass)
-                )
-                daughter = [(1.0, daughter)]
-            elif isinstance(daughter_name, dict):
-                daughter = _recursively_traverse(
-                    daughter_name, mass_converter, particle_model_map, tolerance, preexisting_particles
-                )
-            else:
-                raise TypeError(
-                    f'Expected elements in decaychain["fs"] to only be str or dict '
-                    f"but found an instance of type {type(daughter_name)}"
-                )
-            daughter_gens.append(daughter)
-        for daughter_combination in itertools.product(*daughter_gens):
-            p = float(np.prod([decay[0] for decay in daughter_combination])) * dm_probability
-            if is_top_particle:
-                mother_mass = float(pdg.lookup(original_mother_name).mass)
-            else:
-                if "zfit" in dm:
-                    mass_func = dm["zfit"]
-                elif original_mother_name in particle_model_map:
-                    mass_func = particle_model_map[original_mother_name]
-                else:
-                    mass_func = GenMultiDecay.DEFAULT_MASS_FUNC
-                mother_mass = _get_particle_mass(
-                    original_mother_name, mass_converter=mass_converter, mass_func=mass_func, tolerance=tolerance
-                )
-            one_decay = _clone(GenParticle(mother_name, mother_mass)).set_children(
-                *(_clone(decay[1]) for decay in daughter_combination)
-            )
-            all_decays.append((p, one_decay))
-    return all_decays
+    namer = _Namer()
+    is_top = preexisting_particles is None
+    if not is_top:
+        namer.taken = preexisting_particles
+    return _expand(decaychain, mass_converter, particle_model_map, tolerance, namer, is_top)
 
 
 def _clone(part: GenParticle) -> GenParticle:
-    """Daughter objects are shared between the combinations of ``itertools.product``; every decay tree
-    gets its own copies so that compiled kernels and ``generate`` latches are per tree."""
+    """Templates are shared between the combinations of ``itertools.product``; every decay tree gets its own
+    particle objects so that compiled kernels and ``generate`` latches are per tree."""
     new = GenParticle(part.name, part._mass_val)
     if part.children:
         new.children = tuple(_clone(c) for c in part.children)
