@@ -217,3 +217,27 @@ def test_kinematics_helpers():
     np.testing.assert_allclose(out, orc.lorentz_boost(vec, b), rtol=1e-13, atol=1e-10)
     same = _np(kin.lorentz_boost(vec, np.zeros((1, 3))))
     np.testing.assert_array_equal(same, vec)
+
+
+def test_launch_is_cuda_graph_capturable():
+    """The launch is a plain asynchronous kernel launch on the current stream, so a loop of generations can be
+    captured once in a CUDA graph and replayed (streams and graphs instead of a tracing compiler)."""
+    comp = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3).compile()
+    n = 4096
+    dev = torch.device("cuda")
+    outs = [{"weights": torch.empty((n,), dtype=torch.float64, device=dev),
+             "particles": torch.empty((3, n, 4), dtype=torch.float64, device=dev)} for _ in range(3)]
+    err = torch.zeros((1,), dtype=torch.int32, device=dev)
+    comp.launch(n, 5, out=outs[0], err=err)  # warm-up outside the capture (occupancy query, module load)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for k, out in enumerate(outs):
+            comp.launch(n, 5, first_event=k * n, out=out, err=err)
+    for out in outs:
+        out["weights"].zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    w, _, p, _ = comp.launch(3 * n, 5)
+    assert torch.equal(torch.cat([o["weights"] for o in outs]), w)
+    assert torch.equal(torch.cat([o["particles"] for o in outs], dim=1), p)
