@@ -170,10 +170,17 @@ def test_jit_compiled_tree():
     desc = D.flat_desc(11, masses=masses)
     tree = D.to_oracle(desc)
     ref_w, ref_p = orc.generate(tree, n, uniform_table(8, 0, n, orc.n_draws(tree)))
-    w, p = D.to_gen(desc).generate(n, seed=8)
-    np.testing.assert_allclose(_np(w), ref_w, rtol=1e-11)
-    for name in ref_p:
-        assert np.max(np.abs(_np(p[name]) - ref_p[name])) / B0_MASS <= 1e-12
+    for exact in (False, True):  # the exact variant is JIT-compiled with --fmad=false
+        w, p = D.to_gen(desc).generate(n, seed=8, exact=exact)
+        np.testing.assert_allclose(_np(w), ref_w, rtol=1e-11)
+        for name in ref_p:
+            assert np.max(np.abs(_np(p[name]) - ref_p[name])) / B0_MASS <= 1e-12
+    # the weights-only mask kernel of the unweighting path is JIT-compiled for this tree as well
+    from phasespace_b200.unweight import generate_unweighted
+
+    w_fast, _ = D.to_gen(desc).generate(n, seed=8)
+    parts, idx, w_acc = generate_unweighted(D.to_gen(desc), n, 8, w_bound=float(ref_w.max()) * 1.01)
+    assert 0 < len(idx) < n and torch.equal(w_acc, w_fast[idx])
     chain = ("B", 5279.58, "fixed", 0.0, [
         ("X", 1500.0, "relbw", 100.0, [("a", 139.57, "fixed", 0.0, []), ("b", 493.677, "fixed", 0.0, [])]),
         ("Y", 2000.0, "gauss", 50.0, [("c", 139.57, "fixed", 0.0, []), ("d", 139.57, "fixed", 0.0, []), ("e", 0.0, "fixed", 0.0, [])]),
