@@ -275,6 +275,25 @@ def run_b200(args, rank, local_rank, world):
                "d2h_bytes_per_step": BYTES_PER_EVENT * e2e_n, "steps": e2e_steps, "events_per_gpu_per_step": e2e_n,
                "api": "GenParticle.generate_host -> ps_generate_host (chunked generate + async D2H into pinned host memory)",
                "checksum_w0": float(w_host[0])}
+    # ---- supplementary: the GPU-consumer case through the public API -- events stay in HBM for a device-side
+    # consumer (a fit on the same GPU); per step only a scalar metric (mean weight) is read back to the host
+    e2e_device = None
+    if not args.no_e2e:
+        decay.generate(n, seed=args.seed)
+        barrier()
+        dev_steps = max(1, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for k in range(dev_steps):
+            w_dev, parts_dev = decay.generate(n, seed=args.seed + k)
+            mean_w = float(w_dev.mean().item())
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_device = {"value": world * n * dev_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": 0,
+                      "d2h_bytes_per_step": 8, "steps": dev_steps, "mean_w": mean_w,
+                      "api": "GenParticle.generate (allocates outputs) + weights.mean().item(); events stay in HBM"}
+        del w_dev, parts_dev
     sampler.stop()
 
     if rank == 0:
@@ -305,6 +324,8 @@ def run_b200(args, rank, local_rank, world):
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if e2e_device is not None:
+            line["e2e_device_consumer"] = e2e_device
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
