@@ -13,7 +13,8 @@ using psk::Pt;
     {#__VA_ARGS__, PS_VARIANT_GENERATE, B, D, PS_EXACT, (const void*)&psk::genbod_kernel<__VA_ARGS__, B != 0, D != 0, PS_EXACT>},
 #define PS_REG(...)                                                                                              \
     PS_GEN(0, 0, __VA_ARGS__) PS_GEN(0, 1, __VA_ARGS__) PS_GEN(1, 0, __VA_ARGS__) PS_GEN(1, 1, __VA_ARGS__)      \
-    {#__VA_ARGS__, PS_VARIANT_MASK, 0, 0, PS_EXACT, (const void*)&psk::genbod_mask_kernel<__VA_ARGS__, false, PS_EXACT>},
+    {#__VA_ARGS__, PS_VARIANT_MASK, 0, 0, PS_EXACT, (const void*)&psk::genbod_mask_kernel<__VA_ARGS__, false, PS_EXACT>},   \
+    {#__VA_ARGS__, PS_VARIANT_HIST, 0, 0, PS_EXACT, (const void*)&psk::genbod_hist_kernel<__VA_ARGS__, false, PS_EXACT>},
 
 static const PsAotEntry kTable[] = {
 #include "ps_aot_trees.inc"

@@ -370,6 +370,9 @@ int jit_compile(const KernelKey& key, const void** fn_out) {
     if (key.variant == PS_VARIANT_GENERATE) {
         src += "extern \"C\" __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) ps_jit_kernel(const __grid_constant__ PsParams prm) {\n"
                "  psk::genbod_body<" + key.sig + ", " + (key.boost ? "true" : "false") + ", " + (key.dbg ? "true" : "false") + ">(prm);\n}\n";
+    } else if (key.variant == PS_VARIANT_HIST) {
+        src += "extern \"C\" __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) ps_jit_kernel(const __grid_constant__ PsParams prm, const __grid_constant__ psk::PsHistParams h) {\n"
+               "  psk::genbod_hist_body<" + key.sig + ", " + (key.boost ? "true" : "false") + ">(prm, h);\n}\n";
     } else {
         src += "extern \"C\" __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) ps_jit_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask, int* tile_counts) {\n"
                "  psk::genbod_mask_body<" + key.sig + ", " + (key.boost ? "true" : "false") + ">(prm, w_bound, mask, tile_counts);\n}\n";
@@ -739,6 +742,48 @@ extern "C" int ps_unweight_index(const uint32_t* mask, const int64_t* tile_offse
     long long grid = (long long)sms * 8 < tiles ? (long long)sms * 8 : tiles;
     index_kernel<<<(int)grid, PS_BLOCK, 0, (cudaStream_t)stream>>>(mask, (const long long*)tile_offsets, first_event, n_events, (long long*)event_index);
     PS_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- fused histograms
+namespace {
+struct PsHistParamsHost {  // must match psk::PsHistParams (ps_kernel.cuh)
+    int n_bins;
+    double p_lo, p_inv_width, e_lo, e_inv_width, w_inv_width;
+    double* hist;
+};
+}  // namespace
+
+extern "C" int ps_histogram(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events,
+                            const double* boost_to, int64_t boost_rows, int32_t n_bins, double p_lo, double p_hi,
+                            double e_lo, double e_hi, double* hist, int32_t* err_flag, uint32_t flags, void* stream) {
+    if (!tree || !hist) return fail(PS_E_INVALID, "null argument");
+    if (tree->n_user > 0) return fail(PS_E_INVALID, "ps_histogram does not take user-mass trees");
+    if (n_bins < 1 || !(p_hi > p_lo) || !(e_hi > e_lo)) return fail(PS_E_INVALID, "bad histogram binning");
+    const size_t smem = (size_t)(4 * tree->n_particles + 1) * (size_t)n_bins * sizeof(double);
+    if (smem > 96 * 1024) return fail(PS_E_INVALID, "histograms need %zu bytes of shared memory per CTA (limit 96 KiB): use fewer bins", smem);
+    PsParams p;
+    int rc = fill_params(tree, p, seed, first_event, nullptr, n_events, boost_to, boost_rows, nullptr, nullptr, nullptr,
+                         nullptr, nullptr, 0, nullptr, err_flag, flags | PS_GEN_NORMALIZE);
+    if (rc) return rc;
+    if (n_events == 0) return 0;
+    const void* fn = nullptr;
+    rc = get_kernel(tree, PS_VARIANT_HIST, boost_to ? 1 : 0, 0, (flags & PS_GEN_EXACT) ? 1 : 0, &fn);
+    if (rc) return rc;
+    if (smem > 48 * 1024) PS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0, per_sm = 0;
+    PS_CUDA(cudaGetDevice(&dev));
+    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PS_BLOCK, smem) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 1;
+    }
+    const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
+    const int grid = (int)((long long)sms * per_sm < tiles ? (long long)sms * per_sm : tiles);
+    PsHistParamsHost h{n_bins, p_lo, n_bins / (p_hi - p_lo), e_lo, n_bins / (e_hi - e_lo), n_bins / (1.0 + 1e-8), hist};
+    void* args[] = {&p, &h};
+    PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, smem, (cudaStream_t)stream));
     g_launches.fetch_add(1);
     return 0;
 }

@@ -743,5 +743,83 @@ __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS)
     genbod_mask_body<Tree, BOOST>(prm, w_bound, mask, tile_counts);
 }
 
+// ------------------------------------------------------------------ fused weighted histograms
+// The consumer of the reference's own physics tests (tests/test_physics.py:96-107): a weighted histogram of every
+// coordinate of every particle (momentum components on [p_lo, p_hi), energies on [e_lo, e_hi), weight = the
+// normalised event weight) plus an unweighted histogram of the weights on [0, 1 + 1e-8).  Events are generated
+// exactly as by genbod_kernel but never stored: each CTA accumulates into shared memory (fp64 shared atomics)
+// and adds its histograms to the global ones once at the end, so the kernel is bound by the fp64 pipe, not HBM.
+struct PsHistParams {
+    int n_bins;
+    double p_lo, p_inv_width, e_lo, e_inv_width, w_inv_width;
+    double* hist;  // (4 P + 1, n_bins): rows px,py,pz,E of slot 0, ... , then the weight histogram
+};
+
+template <class C, int S>
+__device__ __forceinline__ void hist_particle(const C& c, const PsHistParams& h, double* sh, double w) {
+    const double v[4] = {c.px[S], c.py[S], c.pz[S], c.en[S]};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double t = (v[k] - (k == 3 ? h.e_lo : h.p_lo)) * (k == 3 ? h.e_inv_width : h.p_inv_width);
+        const int bin = (int)floor(t);
+        if (t >= 0.0 && bin < h.n_bins) atomicAdd(&sh[(4 * S + k) * h.n_bins + bin], w);
+    }
+}
+template <class C, int... S>
+__device__ __forceinline__ void hist_particles(const C& c, const PsHistParams& h, double* sh, double w, Seq<S...>) {
+    (hist_particle<C, S>(c, h, sh, w), ...);
+}
+
+template <class Tree, bool BOOST>
+__device__ __forceinline__ void genbod_hist_body(const PsParams& prm, const PsHistParams& h) {
+    constexpr int P = Tree::n_below;
+    constexpr bool WMAX_PER_EVENT = BOOST || Tree::resonant_leaf_below;
+    extern __shared__ double sh[];
+    const int n_cells = (4 * P + 1) * h.n_bins;
+    for (int k = threadIdx.x; k < n_cells; k += PS_BLOCK) sh[k] = 0.0;
+    __syncthreads();
+    bool bad_any = false;
+    const long long n = prm.n_events;
+    for (long long tile = blockIdx.x; tile * PS_BLOCK < n; tile += gridDim.x) {
+        const long long i = tile * PS_BLOCK + threadIdx.x;
+        if (i < n) {
+            Ctx<P, false> c;
+            c.seed = prm.seed;
+            c.event = prm.first_event + (unsigned long long)i;
+            c.dbg_row = nullptr;
+            c.bad = false;
+            double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
+            if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
+            const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
+            double w_max;
+            if constexpr (WMAX_PER_EVENT) {
+                const double M = BOOST ? kin_mass(bx, by, bz, be) : prm.mass[0];
+                if constexpr (Tree::has_grandchildren)
+                    w_max = recurse_w_max<Tree>(c, M);
+                else
+                    w_max = node_w_max<Tree>(c, M, MakeSeq<Tree::nch>{});
+            } else {
+                w_max = prm.wmax_const;
+            }
+            const double w_norm = w / w_max;
+            hist_particles(c, h, sh, w_norm, MakeSeq<P>{});
+            const int wb = (int)floor(w_norm * h.w_inv_width);
+            if (w_norm >= 0.0 && wb < h.n_bins) atomicAdd(&sh[4 * P * h.n_bins + wb], 1.0);
+            bad_any |= c.bad;
+        }
+    }
+    if (bad_any) *prm.err_flag = PS_ERR_FORBIDDEN;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_cells; k += PS_BLOCK)
+        if (sh[k] != 0.0) atomicAdd(&h.hist[k], sh[k]);
+}
+
+template <class Tree, bool BOOST, int EXACT>
+__global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS)
+    genbod_hist_kernel(const __grid_constant__ PsParams prm, const __grid_constant__ PsHistParams h) {
+    static_assert(EXACT == PS_EXACT, "variant tag must match the translation unit");
+    genbod_hist_body<Tree, BOOST>(prm, h);
+}
+
 }  // namespace psk
 #endif

@@ -5,6 +5,7 @@
 
 #define PS_VARIANT_GENERATE 0 /* genbod_kernel: weights + 4-vectors */
 #define PS_VARIANT_MASK 1     /* genbod_mask_kernel: weights only -> accept mask (unweighting pass 1) */
+#define PS_VARIANT_HIST 2     /* genbod_hist_kernel: fused weighted histograms, nothing stored */
 
 struct PsAotEntry {
     const char* signature; /* canonical tree type, e.g. "Pt<-1,0,0,Pt<0,0,-1>,Pt<1,0,-1>>" */

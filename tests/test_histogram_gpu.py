@@ -1,0 +1,60 @@
+"""Fused weighted histograms (ps_histogram) equal the reference-test recipe applied to the stored events:
+make_norm_histo(coordinate, weights=weights) for every coordinate, and the weight histogram on (0, 1 + 1e-8)."""
+
+import numpy as np
+import pytest
+import torch
+
+import phasespace_b200 as phasespace
+from phasespace_b200.histogram import generate_histograms
+
+from .helpers import decays as D
+from .helpers.plotting import make_norm_histo
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference_recipe(weights, parts):
+    w = weights.cpu().numpy()
+    out = {}
+    for name, vec in parts.items():
+        v = vec.cpu().numpy()
+        out[name] = np.stack([make_norm_histo(v[:, c], range_=(-3000 if c != 3 else 0, 3000), weights=w) for c in range(4)])
+    return out, make_norm_histo(w, range_=(0, 1 + 1e-8))
+
+
+@pytest.mark.parametrize("desc", [D.flat_desc(3), D.flat_desc(4), D.kstar_gamma_desc("relbw"), D.flat_desc(11)],
+                         ids=["3body", "4body", "kstar_gamma", "11body_jit"])
+def test_fused_histograms_match_stored_events(desc):
+    n, seed = 300_000, 21
+    gen = D.to_gen(desc)
+    weights, parts = gen.generate(n, seed=seed)
+    ref_parts, ref_w = _reference_recipe(weights, parts)
+    got_parts, got_w = generate_histograms(gen, n, seed=seed)
+    assert list(got_parts) == list(parts)
+    for name in parts:
+        np.testing.assert_allclose(got_parts[name].cpu().numpy(), ref_parts[name], rtol=1e-9, atol=1e-15, err_msg=name)
+    np.testing.assert_allclose(got_w.cpu().numpy(), ref_w, rtol=1e-12, atol=0)
+    # un-normalised: every in-range event is counted once in the weight histogram, chunking does not matter
+    raw_parts, raw_w = generate_histograms(gen, n, seed=seed, normalize=False, chunk_events=70_001)
+    assert float(raw_w.sum()) == n
+    raw2_parts, raw2_w = generate_histograms(gen, n, seed=seed, normalize=False)
+    assert torch.equal(raw_w, raw2_w)
+    for name in parts:
+        np.testing.assert_allclose(raw_parts[name].cpu().numpy(), raw2_parts[name].cpu().numpy(), rtol=1e-11)
+
+
+def test_fused_histograms_with_boost():
+    n, seed = 100_000, 4
+    rng = np.random.default_rng(2)
+    p = rng.normal(0, 1500.0, (n, 3))
+    boost = np.concatenate([p, np.sqrt((p * p).sum(1, keepdims=True) + D.B0_MASS**2)], axis=1)
+    decay = phasespace.nbody_decay(D.B0_MASS, [D.PION_MASS] * 3)
+    weights, parts = decay.generate(n, boost_to=boost, seed=seed)
+    ref_parts, ref_w = _reference_recipe(weights, parts)
+    got_parts, got_w = generate_histograms(decay, n, seed=seed, boost_to=boost)
+    for name in parts:
+        np.testing.assert_allclose(got_parts[name].cpu().numpy(), ref_parts[name], rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(got_w.cpu().numpy(), ref_w, rtol=1e-12)
+    with pytest.raises(ValueError):
+        generate_histograms(decay, n, seed=seed, bins=5000)

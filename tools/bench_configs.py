@@ -70,3 +70,10 @@ parts, idx, w = generate_unweighted(ten, n5, 1, w_bound=bound)
 print(json.dumps({"config": "5b: 10-body accept-reject unweighting (mask+scan+index+regenerate)", "n_candidates": n5,
                   "w_bound": bound, "accepted": int(idx.numel()), "ms": ms, "candidates_per_s": n5 / ms * 1e3,
                   "accepted_per_s": idx.numel() / ms * 1e3, "max_w_seen": float(w.max())}), flush=True)
+
+# fused histograms: nothing but 13 x 100 doubles leaves the chip
+from phasespace_b200.histogram import generate_histograms
+three = ps.nbody_decay(B0, [PI] * 3)
+ms = timed(lambda: generate_histograms(three, n8, seed=1), reps=5)
+print(json.dumps({"config": "2h: B0->3pi fused weighted histograms (13 x 100 bins), nothing stored", "n_events": n8, "ms": ms,
+                  "events_per_s": n8 / ms * 1e3}), flush=True)
