@@ -168,8 +168,8 @@ def relbw_cdf(x, m, gamma):
     return c_atan * (np.arctan((x - p) / q) + np.arctan((x + p) / q)) + c_log * np.log((x2r + tpx) / (x2r - tpx))
 
 
-RELBW_MAX_ITERS = 8
-RELBW_LAST_STEP = 1e-7
+RELBW_MAX_ITERS = 40
+RELBW_LAST_STEP = 1e-9
 
 
 def _relbw_consts(m, gamma):
@@ -196,7 +196,8 @@ def sample_mass(kind, m, width, lo, hi, u):
       GAUSS  truncated normal(mu=m, sigma=width)  (zfit Gauss / tfp TruncatedNormal)
       BW     Cauchy  ~ 1/(1+((x-m)/width)^2)     (zfit Cauchy, gamma=width)
       RELBW  ~ 1/((x^2-m^2)^2 + m^2 width^2)      (zfit_physics RelativisticBreitWigner)
-    The same formulas are used by the kernel (phasespace_b200/csrc/ps_samplers.cuh).
+    The kernel (phasespace_b200/csrc/ps_samplers.cuh) solves the same equations
+    ``x = F^-1(F(lo) + u (F(hi) - F(lo)))`` with solvers of its own.
     """
     lo, hi, u = (np.asarray(v, dtype=np.float64) for v in (lo, hi, u))
     if kind == GAUSS:
@@ -221,14 +222,19 @@ def sample_mass(kind, m, width, lo, hi, u):
         f_hi = _relbw_cdf_t(consts, t_hi, hi, (hi - p) / q)
         target = f_lo + u * (f_hi - f_lo)
         t = t_lo + u * (t_hi - t_lo)
+        # Newton in t = atan((x-p)/q), in which the CDF is nearly linear, run to full convergence: every event
+        # takes one more step after its first step below RELBW_LAST_STEP (the error left after a step s is
+        # ~C s^2 with C up to a few hundred in the far tail, so that last step lands on the rounding floor).
         active = np.ones(np.shape(t), dtype=bool)
-        for _ in range(RELBW_MAX_ITERS):  # Newton in t = atan((x-p)/q): the CDF is nearly linear in t
+        last = np.zeros(np.shape(t), dtype=bool)
+        for _ in range(RELBW_MAX_ITERS):
             tt = np.tan(t)
             x = p + q * tt
             g = _relbw_cdf_t(consts, t, x, tt) - target
             step = g * q * ((x + p) * (x + p) + q * q)
             t = np.where(active, np.minimum(np.maximum(t - step, t_lo), t_hi), t)
-            active = active & ~(np.abs(step) < RELBW_LAST_STEP)  # the error left after a step s is ~0.03 s^2
+            active = active & ~last
+            last = last | (np.abs(step) < RELBW_LAST_STEP)
             if not active.any():
                 break
         x = p + q * np.tan(t)

@@ -182,6 +182,52 @@ double host_recurse_w_max(const ps_tree& t, int node, double parent_mass) {
     return w * host_get_w_max(avail, masses);
 }
 
+// Sampler constants that depend only on (mass, width): PsParams::sc.
+void host_sampler_constants(int kind, double mass, double width, double out[5]) {
+    for (int k = 0; k < 5; ++k) out[k] = 0.0;
+    if (kind == PS_MASS_GAUSS || kind == PS_MASS_BW) {
+        out[0] = 1.0 / width;
+    } else if (kind == PS_MASS_RELBW) {
+        const double a = mass * mass, b = mass * width;
+        const double rho = std::sqrt(a * a + b * b);
+        const double p = std::sqrt(0.5 * (rho + a)), q = std::sqrt(0.5 * (rho - a));
+        out[0] = p;
+        out[1] = q;
+        out[2] = 2.0 * p / q;
+        out[3] = q / (2.0 * p);
+        out[4] = 1.0 / (out[2] * out[2] + 4.0);
+    }
+}
+
+// Sampler constants that depend on the limits [lo, hi] as well: PsParams::lim (same equations as
+// ps_samplers.cuh: sample_gauss / sample_cauchy / relbw_limits).
+void host_sampler_limits(int kind, double mass, double width, const double sc[5], double lo, double hi, double out[4]) {
+    for (int k = 0; k < 4; ++k) out[k] = 0.0;
+    if (kind == PS_MASS_BW) {
+        out[0] = std::atan((lo - mass) / width);
+        out[1] = std::atan((hi - mass) / width) - out[0];
+    } else if (kind == PS_MASS_GAUSS) {
+        const double alpha = (lo - mass) / width, beta = (hi - mass) / width;
+        const bool flip = alpha > 0.0;
+        const double a_ = flip ? -beta : alpha, b_ = flip ? -alpha : beta;
+        const double ca = 0.5 * std::erfc(-a_ * M_SQRT1_2), cb = 0.5 * std::erfc(-b_ * M_SQRT1_2);
+        out[0] = ca;
+        out[1] = cb - ca;
+        out[2] = flip ? 1.0 : 0.0;
+    } else if (kind == PS_MASS_RELBW) {
+        const double p = sc[0], q = sc[1], kappa = sc[2];
+        const double z_lo = (lo - p) / q, z_hi = (hi - p) / q;
+        auto G = [&](double z) {
+            const double y = z + kappa;
+            return std::atan(z) + std::atan(y) + std::log((y * y + 1.0) / (z * z + 1.0)) / kappa;
+        };
+        out[0] = std::atan(z_lo);
+        out[1] = std::atan(z_hi) - out[0];
+        out[2] = G(z_lo);
+        out[3] = G(z_hi) - out[2];
+    }
+}
+
 }  // namespace
 
 extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tree** out) {
@@ -242,6 +288,11 @@ extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tre
         t->base.width[s1] = nodes[i].width;
         t->min_mass[i] = recurse_stable(*t, i);
         t->base.min_mass[s1] = t->min_mass[i];
+        {
+            double sc[5];
+            host_sampler_constants(nodes[i].kind, nodes[i].mass, nodes[i].width, sc);
+            for (int k = 0; k < 5; ++k) t->base.sc[k][s1] = sc[k];
+        }
         if (nodes[i].kind == PS_MASS_USER) {
             t->user_col[i] = t->n_user++;
             t->base.user_col[s1] = t->user_col[i];
@@ -261,6 +312,29 @@ extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tre
                 t->user_col[i] = col;
                 t->base.user_col[s + 1] = col++;
             }
+        }
+    }
+    // Event-independent limits of the first non-fixed child of a top particle at rest (phasespace.py:342-352:
+    // max_mass = M - sum of the fixed children, min_mass = recurse_stable): see PsParams::lim.
+    {
+        double fs = 0.0;
+        bool first = true;
+        int first_nonfixed = -1;
+        for (int c : t->children[t->top]) {
+            if (nodes[c].kind == PS_MASS_FIXED) {
+                fs = first ? nodes[c].mass : fs + nodes[c].mass;
+                first = false;
+            } else if (first_nonfixed < 0) {
+                first_nonfixed = c;
+            }
+        }
+        if (first_nonfixed >= 0 && is_sampled(nodes[first_nonfixed].kind)) {
+            const int c = first_nonfixed, s1 = t->slot[c] + 1;
+            double sc[5];
+            for (int k = 0; k < 5; ++k) sc[k] = t->base.sc[k][s1];
+            t->base.lim_slot1 = s1;
+            host_sampler_limits(nodes[c].kind, nodes[c].mass, nodes[c].width, sc, t->min_mass[c],
+                                nodes[t->top].mass - fs, t->base.lim);
         }
     }
     t->signature = emit_signature(*t, t->top);
@@ -750,6 +824,7 @@ extern "C" int ps_unweight_index(const uint32_t* mask, const int64_t* tile_offse
 namespace {
 struct PsHistParamsHost {  // must match psk::PsHistParams (ps_kernel.cuh)
     int n_bins;
+    int rep_log2;
     double p_lo, p_inv_width, e_lo, e_inv_width, w_inv_width;
     double* hist;
 };
@@ -761,8 +836,13 @@ extern "C" int ps_histogram(const ps_tree* tree, uint64_t seed, uint64_t first_e
     if (!tree || !hist) return fail(PS_E_INVALID, "null argument");
     if (tree->n_user > 0) return fail(PS_E_INVALID, "ps_histogram does not take user-mass trees");
     if (n_bins < 1 || !(p_hi > p_lo) || !(e_hi > e_lo)) return fail(PS_E_INVALID, "bad histogram binning");
-    const size_t smem = (size_t)(4 * tree->n_particles + 1) * (size_t)n_bins * sizeof(double);
+    size_t smem = (size_t)(4 * tree->n_particles + 1) * (size_t)n_bins * sizeof(double);
     if (smem > 96 * 1024) return fail(PS_E_INVALID, "histograms need %zu bytes of shared memory per CTA (limit 96 KiB): use fewer bins", smem);
+    int rep_log2 = 0;  // interleaved copies per cell (PsHistParams): as many as fit in ~100 KiB, at most 8
+    while (rep_log2 < 3 && (smem << 1) <= 100 * 1024) {
+        smem <<= 1;
+        ++rep_log2;
+    }
     PsParams p;
     int rc = fill_params(tree, p, seed, first_event, nullptr, n_events, boost_to, boost_rows, nullptr, nullptr, nullptr,
                          nullptr, nullptr, 0, nullptr, err_flag, flags | PS_GEN_NORMALIZE);
@@ -781,7 +861,7 @@ extern "C" int ps_histogram(const ps_tree* tree, uint64_t seed, uint64_t first_e
     }
     const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
     const int grid = (int)((long long)sms * per_sm < tiles ? (long long)sms * per_sm : tiles);
-    PsHistParamsHost h{n_bins, p_lo, n_bins / (p_hi - p_lo), e_lo, n_bins / (e_hi - e_lo), n_bins / (1.0 + 1e-8), hist};
+    PsHistParamsHost h{n_bins, rep_log2, p_lo, n_bins / (p_hi - p_lo), e_lo, n_bins / (e_hi - e_lo), n_bins / (1.0 + 1e-8), hist};
     void* args[] = {&p, &h};
     PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, smem, (cudaStream_t)stream));
     g_launches.fetch_add(1);
@@ -791,12 +871,13 @@ extern "C" int ps_histogram(const ps_tree* tree, uint64_t seed, uint64_t first_e
 // ---------------------------------------------------------------------------------- small kernels
 namespace {
 
-__global__ void __launch_bounds__(PS_BLOCK) sample_mass_kernel(int kind, double mass, double width, const double* lo,
-                                                               const double* hi, long long n, unsigned long long seed,
-                                                               unsigned long long first_event, double* out) {
+__global__ void __launch_bounds__(PS_BLOCK) sample_mass_kernel(int kind, const __grid_constant__ psk::SamplerConst k,
+                                                               const double* lo, const double* hi, long long n,
+                                                               unsigned long long seed, unsigned long long first_event,
+                                                               double* out) {
     for (long long i = (long long)blockIdx.x * PS_BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * PS_BLOCK) {
         const double u = psk::philox_uniform0(seed, first_event + (unsigned long long)i, 2u);
-        out[i] = psk::sample_mass(kind, mass, width, lo[i], hi[i], u);
+        out[i] = psk::sample_mass<false>(kind, k, nullptr, lo[i], hi[i], u);
     }
 }
 
@@ -851,7 +932,10 @@ extern "C" int ps_sample_mass(int32_t kind, double mass, double width, const dou
     if (!(width > 0.0)) return fail(PS_E_INVALID, "ps_sample_mass: width must be > 0");
     if (!min_mass || !max_mass || !out || n_events < 0) return fail(PS_E_INVALID, "null argument");
     if (n_events == 0) return 0;
-    sample_mass_kernel<<<small_grid(n_events), PS_BLOCK, 0, (cudaStream_t)stream>>>(kind, mass, width, min_mass, max_mass, n_events, seed, first_event, out);
+    double sc[5];
+    host_sampler_constants(kind, mass, width, sc);
+    const psk::SamplerConst k{mass, width, sc[0], sc[1], sc[2], sc[3], sc[4]};
+    sample_mass_kernel<<<small_grid(n_events), PS_BLOCK, 0, (cudaStream_t)stream>>>(kind, k, min_mass, max_mass, n_events, seed, first_event, out);
     PS_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     return 0;

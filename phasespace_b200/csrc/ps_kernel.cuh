@@ -77,6 +77,12 @@ struct Pt {
         for (int i = 0; i < j; ++i) n += s[i] ? 1 : 0;
         return n;
     }
+    __host__ __device__ static constexpr int nonfixed_before(int j) {
+        const bool s[] = {(Ch::kind != PS_KIND_FIXED)..., false};
+        int n = 0;
+        for (int i = 0; i < j; ++i) n += s[i] ? 1 : 0;
+        return n;
+    }
 };
 
 // ------------------------------------------------------------------ per-event state
@@ -134,6 +140,29 @@ __device__ __forceinline__ double pdk_x(double a, double b, double c) {
 }
 __device__ __forceinline__ double pdk(double a, double b, double c) { return sqrt(pdk_x(a, b, c)) / (2.0 * a); }
 
+// Fast variant: the maximum weight of a tree is a product of two-body momenta sqrt(x_i)/(2 a_i) over all decaying
+// nodes; only its reciprocal is needed to normalise the weight, so the factors are multiplied up first --
+// prod(2 a_i) * rsqrt(prod x_i) -- with one reciprocal square root per four factors (x_i ~ M^4: four of them stay
+// far from overflow for any mass scale) instead of a square root and a reciprocal per factor.
+struct WmaxAcc {
+    double rs = 1.0, px = 1.0, pe = 1.0;
+    int cnt = 0, n = 0;
+    __device__ __forceinline__ void add(double x, double two_a) {
+        px = cnt == 0 ? x : px * x;
+        pe = n == 0 ? two_a : pe * two_a;
+        ++n;
+        if (++cnt == 4) flush();
+    }
+    __device__ __forceinline__ void flush() {
+        if (cnt) rs = rs * rsqrt_pos(px);
+        cnt = 0;
+    }
+    __device__ __forceinline__ double inverse() {  // 1 / w_max
+        flush();
+        return pe * rs;
+    }
+};
+
 // phasespace.py:288-298
 template <int N>
 __device__ __forceinline__ double get_w_max(double avail, const double (&m)[N]) {
@@ -142,13 +171,19 @@ __device__ __forceinline__ double get_w_max(double avail, const double (&m)[N]) 
     for (int i = 1; i < N; ++i) {
         emmin = emmin + m[i - 1];
         emmax = emmax + m[i];
-#if PS_EXACT
         w_max = w_max * pdk(emmax, emmin, m[i]);
-#else
-        w_max = w_max * (sqrt_pos(pdk_x(emmax, emmin, m[i])) * (0.5 * rcp_pos(emmax)));
-#endif
     }
     return w_max;
+}
+template <int N>
+__device__ __forceinline__ void get_w_max(double avail, const double (&m)[N], WmaxAcc& acc) {
+    double emmax = avail + m[0], emmin = 0.0;
+#pragma unroll
+    for (int i = 1; i < N; ++i) {
+        emmin = emmin + m[i - 1];
+        emmax = emmax + m[i];
+        acc.add(pdk_x(emmax, emmin, m[i]), emmax + emmax);
+    }
 }
 
 // kinematics.py:122-149, reference operation order.  The reference tests b2 == 0 over the whole
@@ -194,7 +229,9 @@ __device__ __forceinline__ void fixed_sum_one(const PsParams& prm, double& s, bo
     }
 }
 
-template <class Node, int J, class C>
+// TOP_AT_REST: Node is the top particle decaying at rest, so the limits of its first non-fixed child are event
+// independent and come precomputed (PsParams::lim).
+template <class Node, int J, bool TOP_AT_REST, class C>
 __device__ __forceinline__ void assign_mass_one(C& c, const PsParams& prm, long long i, double* m, double& max_mass) {
     using Child = typename Node::template child<J>;
     constexpr int s1 = Child::slot + 1;
@@ -206,20 +243,21 @@ __device__ __forceinline__ void assign_mass_one(C& c, const PsParams& prm, long 
             mass = prm.user_masses[i * prm.n_user + prm.user_col[s1]];
         } else {
             const double u = c.template next<Node::ucol + Node::sampled_before(J)>();
-            mass = sample_mass(Child::kind, prm.mass[s1], prm.width[s1], prm.min_mass[s1], max_mass, u);
+            constexpr bool CONST_LIM = TOP_AT_REST && Node::nonfixed_before(J) == 0;
+            mass = sample_mass<CONST_LIM>(Child::kind, sampler_const(prm, s1), prm.lim, prm.min_mass[s1], max_mass, u);
         }
         max_mass = max_mass - mass;  // phasespace.py:352
         m[J] = mass;
     }
 }
 
-template <class Node, class C, int... J>
+template <class Node, bool TOP_AT_REST, class C, int... J>
 __device__ __forceinline__ void assign_masses(C& c, const PsParams& prm, long long i, double M, double* m, Seq<J...>) {
     double fs = 0.0;
     bool first = true;
     (fixed_sum_one<Node, J, C>(prm, fs, first), ...);
     double max_mass = M - fs;  // phasespace.py:342
-    (assign_mass_one<Node, J, C>(c, prm, i, m, max_mass), ...);
+    (assign_mass_one<Node, J, TOP_AT_REST, C>(c, prm, i, m, max_mass), ...);
 }
 
 template <int BASE, class C, int... I>
@@ -367,7 +405,7 @@ __device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long 
     }
 
     double m[N];
-    assign_masses<Node>(c, prm, i, M, m, MakeSeq<N>{});
+    assign_masses<Node, REST && Node::slot < 0>(c, prm, i, M, m, MakeSeq<N>{});
     double msum = m[0];
 #pragma unroll
     for (int j = 1; j < N; ++j) msum = msum + m[j];
@@ -487,16 +525,26 @@ __device__ __forceinline__ void acc_leaves_except(const C& c, double& s, Seq<J..
     ((J != SKIP ? acc_leaves_child<Node, J>(c, s) : (void)0), ...);
 }
 
-template <class Node, class C>
-__device__ __forceinline__ double recurse_w_max(const C& c, double parent_mass);
+// ACC is double& (exact: the running product w_max, reference order) or WmaxAcc& (fast).
+template <int N>
+__device__ __forceinline__ void w_max_node(double avail, const double (&m)[N], double& w_max) {
+    w_max = w_max * get_w_max<N>(avail, m);
+}
+template <int N>
+__device__ __forceinline__ void w_max_node(double avail, const double (&m)[N], WmaxAcc& acc) {
+    get_w_max<N>(avail, m, acc);
+}
 
-template <class Node, int J, class C>
-__device__ __forceinline__ void w_max_child(const C& c, double parent_mass, double* masses, double& w_max) {
+template <class Node, class C, class ACC>
+__device__ __forceinline__ void recurse_w_max(const C& c, double parent_mass, ACC& acc);
+
+template <class Node, int J, class C, class ACC>
+__device__ __forceinline__ void w_max_child(const C& c, double parent_mass, double* masses, ACC& acc) {
     using Child = typename Node::template child<J>;
     if constexpr (Child::nch > 0) {
         double others = 0.0;
         acc_leaves_except<Node, J>(c, others, MakeSeq<Node::nch>{});
-        w_max = w_max * recurse_w_max<Child>(c, parent_mass - others);
+        recurse_w_max<Child>(c, parent_mass - others, acc);
         double own = 0.0;
         acc_leaves<Child>(c, own);
         masses[J] = own;
@@ -504,30 +552,60 @@ __device__ __forceinline__ void w_max_child(const C& c, double parent_mass, doub
         masses[J] = c.ms[Child::slot];
     }
 }
-template <class Node, class C, int... J>
-__device__ __forceinline__ void w_max_children(const C& c, double parent_mass, double* masses, double& w_max, Seq<J...>) {
-    (w_max_child<Node, J>(c, parent_mass, masses, w_max), ...);
+template <class Node, class C, class ACC, int... J>
+__device__ __forceinline__ void w_max_children(const C& c, double parent_mass, double* masses, ACC& acc, Seq<J...>) {
+    (w_max_child<Node, J>(c, parent_mass, masses, acc), ...);
 }
-template <class Node, class C>
-__device__ __forceinline__ double recurse_w_max(const C& c, double parent_mass) {
+template <class Node, class C, class ACC>
+__device__ __forceinline__ void recurse_w_max(const C& c, double parent_mass, ACC& acc) {
     constexpr int N = Node::nch;
     double flat = 0.0;
     acc_leaves<Node>(c, flat);
     const double avail = parent_mass - flat;
     double masses[N];
-    double w_max = 1.0;
-    w_max_children<Node>(c, parent_mass, masses, w_max, MakeSeq<N>{});
-    return w_max * get_w_max<N>(avail, masses);
+    w_max_children<Node>(c, parent_mass, masses, acc, MakeSeq<N>{});
+    w_max_node<N>(avail, masses, acc);
 }
 
-template <class Node, class C, int... J>
-__device__ __forceinline__ double node_w_max(const C& c, double M, Seq<J...>) {
+template <class Node, class C, class ACC, int... J>
+__device__ __forceinline__ void node_w_max(const C& c, double M, ACC& acc, Seq<J...>) {
     constexpr int N = Node::nch;
     const double m[N] = {c.ms[Node::template child<J>::slot]...};
     double msum = m[0];
 #pragma unroll
     for (int j = 1; j < N; ++j) msum = msum + m[j];
-    return get_w_max<N>(M - msum, m);
+    w_max_node<N>(M - msum, m, acc);
+}
+
+// Maximum weight of the event (phasespace.py:364 for a flat decay, 571-625 for a chain) as the pair the callers
+// need: INV = 1 / w_max always; W_MAX itself only in the exact variant or when WANT_WMAX asks for it.
+// Event independent (rest frame, fixed leaf masses): the host's constants.
+template <class Tree, bool BOOST, class C>
+__device__ __forceinline__ void event_w_max(const C& c, const PsParams& prm, double bx, double by, double bz, double be,
+                                            bool want_w_max, double& w_max, double& inv) {
+    constexpr bool WMAX_PER_EVENT = BOOST || Tree::resonant_leaf_below;
+    if constexpr (WMAX_PER_EVENT) {
+        const double M = BOOST ? kin_mass(bx, by, bz, be) : prm.mass[0];
+#if PS_EXACT
+        w_max = 1.0;
+        if constexpr (Tree::has_grandchildren)
+            recurse_w_max<Tree>(c, M, w_max);
+        else
+            node_w_max<Tree>(c, M, w_max, MakeSeq<Tree::nch>{});
+        inv = 0.0;  // unused: the exact variant divides by w_max
+#else
+        WmaxAcc acc;
+        if constexpr (Tree::has_grandchildren)
+            recurse_w_max<Tree>(c, M, acc);
+        else
+            node_w_max<Tree>(c, M, acc, MakeSeq<Tree::nch>{});
+        inv = acc.inverse();
+        w_max = want_w_max ? rcp_pos(inv) : 0.0;
+#endif
+    } else {
+        w_max = prm.wmax_const;
+        inv = prm.inv_wmax_const;
+    }
 }
 
 // ------------------------------------------------------------------ stores
@@ -584,10 +662,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <class Tree, bool BOOST, bool DBG>
 __device__ __forceinline__ void genbod_body(const PsParams& prm) {
     constexpr int P = Tree::n_below;
-    constexpr bool WMAX_PER_EVENT = BOOST || Tree::resonant_leaf_below;
     static_assert(P <= PS_MAX_SLOTS, "decay tree too large");
 
-    double st_max = 0.0, st_sum = 0.0, st_sum2 = 0.0, st_wmax = 0.0;
+    double st_max = 0.0, st_sum = 0.0, st_sum2 = 0.0;
+#if PS_EXACT
+    double st_wmax = 0.0;
+#else
+    double st_inv_min = __longlong_as_double(0x7ff0000000000000LL);
+#endif
     bool bad_any = false;
     const long long n = prm.n_events;
     // the shape is a property of the tree (PS_CHUNKED_MAX_P): the host launches accordingly
@@ -608,22 +690,14 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
             double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
             if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
             const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
-            double w_max;
-            if constexpr (WMAX_PER_EVENT) {
-                const double M = BOOST ? kin_mass(bx, by, bz, be) : prm.mass[0];
-                if constexpr (Tree::has_grandchildren)
-                    w_max = recurse_w_max<Tree>(c, M);  // phasespace.py:571-625
-                else
-                    w_max = node_w_max<Tree>(c, M, MakeSeq<Tree::nch>{});  // phasespace.py:364
-            } else {
-                w_max = prm.wmax_const;
-            }
+            double w_max, inv_w_max;
+            event_w_max<Tree, BOOST>(c, prm, bx, by, bz, be, !prm.normalize && prm.weights_max, w_max, inv_w_max);
             double w_out = w;
             if (prm.normalize) {  // phasespace.py:713-717
 #if PS_EXACT
                 w_out = w / w_max;
 #else
-                w_out = WMAX_PER_EVENT ? w * rcp_pos(w_max) : w * prm.inv_wmax_const;
+                w_out = w * inv_w_max;
 #endif
             } else if (prm.weights_max) {
                 prm.weights_max[i] = w_max;
@@ -634,7 +708,11 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
             st_max = fmax(st_max, w_out);
             st_sum += w_out;
             st_sum2 += w_out * w_out;
+#if PS_EXACT
             st_wmax = fmax(st_wmax, w_max);
+#else
+            st_inv_min = fmin(st_inv_min, inv_w_max);  // max w_max = 1 / min (1 / w_max)
+#endif
         }
         }
     }
@@ -645,7 +723,11 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
         st_max = warp_max(st_max);
         st_sum = warp_sum(st_sum);
         st_sum2 = warp_sum(st_sum2);
+#if PS_EXACT
         st_wmax = warp_max(st_wmax);
+#else
+        double st_wmax = warp_max(1.0 / st_inv_min);  // no events: 1/inf = 0
+#endif
         if (lane == 0) {
             red[0][wid] = st_max;
             red[1][wid] = st_sum;
@@ -687,7 +769,6 @@ template <class Tree, bool BOOST>
 __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_bound, unsigned int* mask,
                                                  int* tile_counts) {
     constexpr int P = Tree::n_below;
-    constexpr bool WMAX_PER_EVENT = BOOST || Tree::resonant_leaf_below;
     __shared__ int warp_counts[PS_BLOCK / 32];
     const long long n = prm.n_events;
     bool bad_any = false;
@@ -703,18 +784,14 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
             double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
             if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
             const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
-            double w_max;
-            if constexpr (WMAX_PER_EVENT) {
-                const double M = BOOST ? kin_mass(bx, by, bz, be) : prm.mass[0];
-                if constexpr (Tree::has_grandchildren)
-                    w_max = recurse_w_max<Tree>(c, M);
-                else
-                    w_max = node_w_max<Tree>(c, M, MakeSeq<Tree::nch>{});
-            } else {
-                w_max = prm.wmax_const;
-            }
+            double w_max, inv_w_max;
+            event_w_max<Tree, BOOST>(c, prm, bx, by, bz, be, false, w_max, inv_w_max);
             const double u = philox_uniform0(prm.seed, c.event, 1u);
+#if PS_EXACT
             accept = u * w_bound * w_max < w;
+#else
+            accept = u * w_bound < w * inv_w_max;
+#endif
             bad_any |= c.bad;
         }
         const unsigned int word = __ballot_sync(0xffffffffu, accept);
@@ -749,34 +826,39 @@ __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS)
 // normalised event weight) plus an unweighted histogram of the weights on [0, 1 + 1e-8).  Events are generated
 // exactly as by genbod_kernel but never stored: each CTA accumulates into shared memory (fp64 shared atomics)
 // and adds its histograms to the global ones once at the end, so the kernel is bound by the fp64 pipe, not HBM.
+// fp64 shared-memory atomics are compare-and-swap loops (ATOMS.CAST.SPIN.64) that retry on every collision, so each
+// CTA keeps 2^rep_log2 interleaved copies of every cell and lane l adds to copy l mod 2^rep_log2: lanes of one
+// warp that fall into the same bin mostly hit different copies (adjacent addresses, different banks).
 struct PsHistParams {
     int n_bins;
+    int rep_log2;
     double p_lo, p_inv_width, e_lo, e_inv_width, w_inv_width;
     double* hist;  // (4 P + 1, n_bins): rows px,py,pz,E of slot 0, ... , then the weight histogram
 };
 
 template <class C, int S>
-__device__ __forceinline__ void hist_particle(const C& c, const PsHistParams& h, double* sh, double w) {
+__device__ __forceinline__ void hist_particle(const C& c, const PsHistParams& h, double* sh, int copy, double w) {
     const double v[4] = {c.px[S], c.py[S], c.pz[S], c.en[S]};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const double t = (v[k] - (k == 3 ? h.e_lo : h.p_lo)) * (k == 3 ? h.e_inv_width : h.p_inv_width);
         const int bin = (int)floor(t);
-        if (t >= 0.0 && bin < h.n_bins) atomicAdd(&sh[(4 * S + k) * h.n_bins + bin], w);
+        if (t >= 0.0 && bin < h.n_bins) atomicAdd(&sh[(((4 * S + k) * h.n_bins + bin) << h.rep_log2) + copy], w);
     }
 }
 template <class C, int... S>
-__device__ __forceinline__ void hist_particles(const C& c, const PsHistParams& h, double* sh, double w, Seq<S...>) {
-    (hist_particle<C, S>(c, h, sh, w), ...);
+__device__ __forceinline__ void hist_particles(const C& c, const PsHistParams& h, double* sh, int copy, double w,
+                                               Seq<S...>) {
+    (hist_particle<C, S>(c, h, sh, copy, w), ...);
 }
 
 template <class Tree, bool BOOST>
 __device__ __forceinline__ void genbod_hist_body(const PsParams& prm, const PsHistParams& h) {
     constexpr int P = Tree::n_below;
-    constexpr bool WMAX_PER_EVENT = BOOST || Tree::resonant_leaf_below;
     extern __shared__ double sh[];
     const int n_cells = (4 * P + 1) * h.n_bins;
-    for (int k = threadIdx.x; k < n_cells; k += PS_BLOCK) sh[k] = 0.0;
+    const int copy = threadIdx.x & ((1 << h.rep_log2) - 1);
+    for (int k = threadIdx.x; k < (n_cells << h.rep_log2); k += PS_BLOCK) sh[k] = 0.0;
     __syncthreads();
     bool bad_any = false;
     const long long n = prm.n_events;
@@ -791,27 +873,26 @@ __device__ __forceinline__ void genbod_hist_body(const PsParams& prm, const PsHi
             double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
             if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
             const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
-            double w_max;
-            if constexpr (WMAX_PER_EVENT) {
-                const double M = BOOST ? kin_mass(bx, by, bz, be) : prm.mass[0];
-                if constexpr (Tree::has_grandchildren)
-                    w_max = recurse_w_max<Tree>(c, M);
-                else
-                    w_max = node_w_max<Tree>(c, M, MakeSeq<Tree::nch>{});
-            } else {
-                w_max = prm.wmax_const;
-            }
+            double w_max, inv_w_max;
+            event_w_max<Tree, BOOST>(c, prm, bx, by, bz, be, false, w_max, inv_w_max);
+#if PS_EXACT
             const double w_norm = w / w_max;
-            hist_particles(c, h, sh, w_norm, MakeSeq<P>{});
+#else
+            const double w_norm = w * inv_w_max;
+#endif
+            hist_particles(c, h, sh, copy, w_norm, MakeSeq<P>{});
             const int wb = (int)floor(w_norm * h.w_inv_width);
-            if (w_norm >= 0.0 && wb < h.n_bins) atomicAdd(&sh[4 * P * h.n_bins + wb], 1.0);
+            if (w_norm >= 0.0 && wb < h.n_bins) atomicAdd(&sh[((4 * P * h.n_bins + wb) << h.rep_log2) + copy], 1.0);
             bad_any |= c.bad;
         }
     }
     if (bad_any) *prm.err_flag = PS_ERR_FORBIDDEN;
     __syncthreads();
-    for (int k = threadIdx.x; k < n_cells; k += PS_BLOCK)
-        if (sh[k] != 0.0) atomicAdd(&h.hist[k], sh[k]);
+    for (int k = threadIdx.x; k < n_cells; k += PS_BLOCK) {
+        double v = 0.0;
+        for (int r = 0; r < (1 << h.rep_log2); ++r) v += sh[(k << h.rep_log2) + r];
+        if (v != 0.0) atomicAdd(&h.hist[k], v);
+    }
 }
 
 template <class Tree, bool BOOST, int EXACT>

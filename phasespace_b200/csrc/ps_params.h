@@ -24,6 +24,20 @@ typedef struct PsParams {
     double width[PS_MAX_SLOTS + 1];    /* resonance width (0 for fixed) */
     double min_mass[PS_MAX_SLOTS + 1]; /* recurse_stable(): sum of fixed masses below (phasespace.py:326-333) */
     int user_col[PS_MAX_SLOTS + 1];    /* column in user_masses for PS_KIND_USER */
+    /* sampler constants derived on the host from (mass, width) (ps_api.cu: fill_sampler_constants).
+     *   GAUSS, BW: sc[0] = 1/width
+     *   RELBW:     sc[0] = p, sc[1] = q (roots of the quartic, ps_samplers.cuh), sc[2] = kappa = 2p/q,
+     *              sc[3] = 1/kappa, sc[4] = 1/(kappa^2 + 4) */
+    double sc[5][PS_MAX_SLOTS + 1];
+    /* The first non-fixed child of the top particle, when it is a sampled resonance and the top decays at rest,
+     * has event-independent mass limits [min_mass, M - fixed sum]: everything of its sampler that depends only
+     * on the limits is evaluated once on the host.  lim_slot1 = its slot + 1, or 0 if there is none.
+     *   BW:    lim[0] = atan((lo-m)/w), lim[1] = atan((hi-m)/w) - lim[0]
+     *   GAUSS: lim[0] = Phi(a), lim[1] = Phi(b) - Phi(a), lim[2] = 1 if mirrored (ps_samplers.cuh) else 0
+     *   RELBW: lim[0] = t_lo, lim[1] = t_hi - t_lo, lim[2] = G(lo), lim[3] = G(hi) - G(lo) */
+    int lim_slot1;
+    int lim_pad_;
+    double lim[4];
 
     double wmax_const;     /* event-independent maximum weight (rest frame, fixed leaf masses) */
     double inv_wmax_const; /* its reciprocal */

@@ -4,90 +4,219 @@
 // zfit_physics RelativisticBreitWigner: fromdecay/mass_functions.py:16-102; tfp TruncatedNormal:
 // tests/helpers/decays.py:26-37) sampled one value per event with per-event limits.  Their
 // arithmetic is not in the reference tree; the densities are restated here and sampled by inverse
-// CDF so that a resonance costs exactly one draw (deterministic draw count, no rejection loop, no
-// warp divergence).  oracle/genbod_numpy.py::sample_mass is the CPU statement of the same formulas.
+// CDF so that a resonance costs exactly one draw (deterministic draw count, no rejection loop).
+// oracle/genbod_numpy.py::sample_mass is the CPU statement of the same equations
+// (x = F^-1(F(lo) + u (F(hi) - F(lo)))); the solvers here are built for the B200's fp64 pipe:
+//   * everything that depends only on (mass, width) comes precomputed in the parameter block (PsParams::sc);
+//   * when the limits are event independent (CONST_LIM: the first resonance below a top particle at rest,
+//     i.e. B -> K* gamma) so does everything that depends only on the limits (PsParams::lim);
+//   * tan / far-field atan are range-specialised (ps_fastmath.cuh), and the relativistic Breit-Wigner CDF
+//     is inverted by two fp32 Halley steps on the special-function unit followed by one fp64
+//     fourth-order inverse-series step instead of a data-dependent fp64 Newton loop.
 #ifndef PS_SAMPLERS_CUH_
 #define PS_SAMPLERS_CUH_
 
 #include "ps_params.h"
+#include "ps_fastmath.cuh"
 
 namespace psk {
+
+struct SamplerConst {
+    double m, w;                // pole mass and width
+    double c0, c1, c2, c3, c4;  // PsParams::sc
+};
+
+__device__ __forceinline__ SamplerConst sampler_const(const PsParams& prm, int s1) {
+    return SamplerConst{prm.mass[s1], prm.width[s1], prm.sc[0][s1], prm.sc[1][s1], prm.sc[2][s1], prm.sc[3][s1], prm.sc[4][s1]};
+}
 
 __device__ __forceinline__ double clamp_mass(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
 
 // truncated normal(mu = m, sigma = w) on [lo, hi]
-__device__ __forceinline__ double sample_gauss(double m, double w, double lo, double hi, double u) {
-    const double alpha = (lo - m) / w, beta = (hi - m) / w;
-    const bool flip = alpha > 0.0;  // work in the tail that keeps precision
-    const double a_ = flip ? -beta : alpha, b_ = flip ? -alpha : beta, u_ = flip ? 1.0 - u : u;
-    const double ca = normcdf(a_), cb = normcdf(b_);
-    double z = normcdfinv(ca + u_ * (cb - ca));
+template <bool CONST_LIM>
+__device__ __forceinline__ double sample_gauss(const SamplerConst& k, const double* lim, double lo, double hi, double u) {
+    double ca, dc;
+    bool flip;
+    if constexpr (CONST_LIM) {
+        ca = lim[0], dc = lim[1], flip = lim[2] != 0.0;
+    } else {
+        const double alpha = (lo - k.m) * k.c0, beta = (hi - k.m) * k.c0;
+        flip = alpha > 0.0;  // work in the tail that keeps precision
+        const double a_ = flip ? -beta : alpha, b_ = flip ? -alpha : beta;
+        ca = normcdf(a_);
+        dc = normcdf(b_) - ca;
+    }
+    const double u_ = flip ? 1.0 - u : u;
+    double z = normcdfinv(fma(u_, dc, ca));
     z = flip ? -z : z;
-    return clamp_mass(m + w * z, lo, hi);
+    return clamp_mass(fma(k.w, z, k.m), lo, hi);
 }
 
 // Cauchy ~ 1 / (1 + ((x-m)/w)^2) on [lo, hi]
-__device__ __forceinline__ double sample_cauchy(double m, double w, double lo, double hi, double u) {
-    const double ta = atan((lo - m) / w), tb = atan((hi - m) / w);
-    return clamp_mass(m + w * tan(ta + u * (tb - ta)), lo, hi);
-}
-
-struct RelBwConst {
-    double a, b, rho, p, q, c_atan, c_log;
-};
-
-__device__ __forceinline__ RelBwConst relbw_const(double m, double w) {
-    RelBwConst k;
-    k.a = m * m;
-    k.b = m * w;
-    k.rho = sqrt(k.a * k.a + k.b * k.b);
-    k.p = sqrt(0.5 * (k.rho + k.a));
-    k.q = sqrt(0.5 * (k.rho - k.a));
-    k.c_atan = 1.0 / (4.0 * k.rho * k.q);
-    k.c_log = 1.0 / (8.0 * k.rho * k.p);
-    return k;
-}
-
-// The antiderivative of 1/((x^2-m^2)^2 + m^2 w^2): the quartic factors as (x^2-2px+rho)(x^2+2px+rho) and
-// partial fractions give  F(x) = [atan((x-p)/q) + atan((x+p)/q)] / (4 rho q) + ln((x^2+2px+rho)/(x^2-2px+rho)) / (8 rho p).
-#define PS_RELBW_MAX_ITERS 8
-#define PS_RELBW_LAST_STEP 1e-7
-
-// ~ 1/((x^2-m^2)^2 + m^2 w^2) on [lo, hi].  Newton in t = atan((x-p)/q), in which the CDF is nearly linear
-// (its dominant term is t / (4 rho q)).  With x = p + q tan t the first arctangent of the CDF is t itself,
-// (x-p)^2 + q^2 = q^2 sec^2 t, and the Newton step  g * D(x) / (q sec^2 t)  collapses to  g * q * A  with
-// A = (x+p)^2 + q^2: one tan, one atan, one log per iteration.  Convergence is quadratic (measured: the error
-// left after a step s is ~0.03 s^2), so the iteration stops right after applying a step below 1e-7 rad
-// (typically the third), or after PS_RELBW_MAX_ITERS.
-__device__ __forceinline__ double relbw_cdf_t(const RelBwConst& k, double t, double x, double tt) {
-    const double A = (x + k.p) * (x + k.p) + k.q * k.q;
-    const double B = k.q * k.q * (1.0 + tt * tt);
-    return k.c_atan * (t + atan((x + k.p) / k.q)) + k.c_log * log(A / B);
-}
-__device__ __forceinline__ double sample_relbw(double m, double w, double lo, double hi, double u) {
-    const RelBwConst k = relbw_const(m, w);
-    const double t_lo = atan((lo - k.p) / k.q), t_hi = atan((hi - k.p) / k.q);
-    const double f_lo = relbw_cdf_t(k, t_lo, lo, (lo - k.p) / k.q), f_hi = relbw_cdf_t(k, t_hi, hi, (hi - k.p) / k.q);
-    const double target = f_lo + u * (f_hi - f_lo);
-    double t = t_lo + u * (t_hi - t_lo);
-#pragma unroll 1
-    for (int it = 0; it < PS_RELBW_MAX_ITERS; ++it) {
-        const double tt = tan(t);
-        const double x = k.p + k.q * tt;
-        const double g = relbw_cdf_t(k, t, x, tt) - target;
-        const double A = (x + k.p) * (x + k.p) + k.q * k.q;
-        const double step = g * k.q * A;
-        t = fmin(fmax(t - step, t_lo), t_hi);
-        if (fabs(step) < PS_RELBW_LAST_STEP) break;  // the error left after a step s is ~0.03 s^2
+template <bool CONST_LIM>
+__device__ __forceinline__ double sample_cauchy(const SamplerConst& k, const double* lim, double lo, double hi, double u) {
+    double ta, dt;
+    if constexpr (CONST_LIM) {
+        ta = lim[0], dt = lim[1];
+    } else {
+        ta = atan((lo - k.m) * k.c0);
+        dt = atan((hi - k.m) * k.c0) - ta;
     }
-    return clamp_mass(k.p + k.q * tan(t), lo, hi);
+    double z, c2;
+    tan_pio2(fma(u, dt, ta), z, c2);
+    return clamp_mass(fma(k.w, z, k.m), lo, hi);
 }
 
-__device__ __forceinline__ double sample_mass(int kind, double m, double w, double lo, double hi, double u) {
+// ------------------------------------------------------------------ relativistic Breit-Wigner
+// Density ~ 1/((x^2-m^2)^2 + m^2 w^2).  The quartic factors as ((x-p)^2+q^2)((x+p)^2+q^2) with
+// rho = sqrt(m^4 + m^2 w^2), p = sqrt((rho+m^2)/2), q = sqrt((rho-m^2)/2).  In z = (x-p)/q, kappa = 2p/q the CDF is,
+// up to a constant factor,
+//     G(z) = atan(z) + atan(z+kappa) + ln(((z+kappa)^2+1)/(z^2+1)) / kappa ,   G'(z) = (kappa^2+4) / ((z^2+1)((z+kappa)^2+1)),
+// and the sample is the root of G(z) = G(z_lo) + u (G(z_hi) - G(z_lo)).  Solver (narrow resonances, kappa >= 16):
+//   1. t = atan z linearises the core (G = t + slowly varying terms): start from the linear interpolation in t and
+//      take two Halley steps in fp32 -- sin, cos, log, reciprocals on the special-function unit, ~30 instructions
+//      each.  That leaves a relative error of 1e-6 .. 1e-2 in z (the far tail, where G'(t) -> 0, is the worst).
+//   2. one evaluation of G in fp64 (range-specialised tan, far-field atan series, one log) and the inverse-function
+//      Taylor series of z(G) to fourth order, whose coefficients are polynomials in z because 1/G' is one:
+//      the truncation error is ~alpha^4/100 relative to the step, alpha = h P'(z)/(kappa^2+4), h = target - G.
+//   3. if |alpha| > 0.01 (not observed with limits inside [0, 10 m]; percent-level when the upper limit is 100 m,
+//      where step 1 is poor) repeat step 2 once or twice while |alpha| <= 0.2, else fall back to the generic solver.
+// Broad resonances (kappa < 16) use the generic Newton iteration with library functions below.
+#define PS_RELBW_MAX_ITERS 8
+#define PS_RELBW_LAST_STEP 1e-9
+#define PS_RELBW_MIN_KAPPA 16.0
+#define PS_RELBW_ALPHA_OK 0.01
+#define PS_RELBW_ALPHA_RETRY 0.2
+
+// slowly varying part of G:  atan(z+kappa) + ln(((z+kappa)^2+1) inv_zz1)/kappa,   inv_zz1 = 1/(z^2+1)
+template <bool FAR>
+__device__ __forceinline__ double relbw_slow(const SamplerConst& k, double z, double inv_zz1) {
+    const double y = z + k.c2;
+    const double at = FAR ? atan_far(y) : atan(y);
+    return fma(log(fma(y, y, 1.0) * inv_zz1), k.c3, at);
+}
+
+__device__ __forceinline__ void relbw_limits(const SamplerConst& k, double lo, double hi, bool far, double& t_lo,
+                                             double& dt, double& g_lo, double& dg) {
+    const double iq = rcp_pos(k.c1);
+    const double z_lo = (lo - k.c0) * iq, z_hi = (hi - k.c0) * iq;
+    t_lo = atan(z_lo);
+    const double t_hi = atan(z_hi);
+    const double i_lo = rcp_pos(fma(z_lo, z_lo, 1.0)), i_hi = rcp_pos(fma(z_hi, z_hi, 1.0));
+    double s_lo, s_hi;
+    if (far) {
+        s_lo = relbw_slow<true>(k, z_lo, i_lo), s_hi = relbw_slow<true>(k, z_hi, i_hi);
+    } else {
+        s_lo = relbw_slow<false>(k, z_lo, i_lo), s_hi = relbw_slow<false>(k, z_hi, i_hi);
+    }
+    dt = t_hi - t_lo;
+    g_lo = t_lo + s_lo;
+    dg = (t_hi + s_hi) - g_lo;
+}
+
+// generic solver: Newton in t with library functions, to full convergence
+static __device__ __noinline__ double relbw_solve_generic(const SamplerConst& k, double t_lo, double t_hi, double t, double target) {
+    const double ik2 = k.c4;
+    bool last = false;
+#pragma unroll 1
+    for (int it = 0; it < 4 * PS_RELBW_MAX_ITERS; ++it) {
+        const double z = tan(t);
+        const double y = z + k.c2;
+        const double b = fma(y, y, 1.0);
+        const double g = t + atan(y) + k.c3 * log(b / fma(z, z, 1.0)) - target;
+        const double step = g * b * ik2;
+        t = fmin(fmax(t - step, t_lo), t_hi);
+        if (last) break;
+        last = fabs(step) < PS_RELBW_LAST_STEP;  // one more step after the first tiny one
+    }
+    return tan(t);
+}
+
+template <bool CONST_LIM>
+__device__ __forceinline__ double sample_relbw(const SamplerConst& k, const double* lim, double lo, double hi, double u) {
+    const bool far = k.c2 >= PS_RELBW_MIN_KAPPA;
+    double t_lo, dt, g_lo, dg;
+    if constexpr (CONST_LIM) {
+        t_lo = lim[0], dt = lim[1], g_lo = lim[2], dg = lim[3];
+    } else {
+        relbw_limits(k, lo, hi, far, t_lo, dt, g_lo, dg);
+    }
+    const double target = fma(u, dg, g_lo);
+    const double t0 = fma(u, dt, t_lo);
+    const double t_hi = t_lo + dt;
+    double z;
+    if (far) {
+        // 1. fp32 Halley steps in t
+        const float kf = (float)k.c2, ikf = (float)k.c3, ik2f = (float)k.c4;
+        const float tlof = (float)t_lo, thif = (float)t_hi, tgf = (float)target;
+        float tf = (float)t0;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            float s, c;
+            __sincosf(tf, &s, &c);
+            c = fmaxf(c, 1e-6f);
+            const float c2 = c * c;
+            const float zf = __fdividef(s, c);
+            const float y = zf + kf;
+            const float iy = __fdividef(1.0f, y);
+            const float iy2 = iy * iy;
+            const float at = 1.5707964f - iy * (1.0f - iy2 * (0.33333334f - 0.2f * iy2));
+            const float b = fmaf(y, y, 1.0f);
+            const float bc = b * c2;
+            const float g = (tf - tgf) + fmaf(__logf(bc), ikf, at);
+            const float n = g * b * ik2f;                 // Newton step
+            const float r = -y * __fdividef(1.0f, bc);    // G''/(2 G') in t
+            const float den = fmaf(-n, r, 1.0f);
+            const float step = den > 0.5f ? __fdividef(n, den) : n;
+            tf = fminf(fmaxf(tf - step, tlof), thif);
+        }
+        // 2./3. fp64: evaluate G once, fourth-order inverse series in z
+        double t = (double)tf;
+        double inv_zz1;
+        tan_pio2(t, z, inv_zz1);
+        bool done = false;
+#pragma unroll 1
+        for (int it = 0; it < 3; ++it) {
+            const double y = z + k.c2;
+            const double A = fma(z, z, 1.0), B = fma(y, y, 1.0);
+            const double G = t + fma(log(B * inv_zz1), k.c3, atan_far(y));
+            const double h = (target - G) * k.c4;   // h / (kappa^2 + 4)
+            const double zy = z * y;
+            const double P1 = 2.0 * fma(z, B, y * A);        // P = A B and its derivatives
+            const double P2 = fma(8.0, zy, 2.0 * (A + B));
+            const double P3 = 12.0 * (y + z);
+            const double d = h * (A * B);                     // Newton step in z
+            const double al = h * P1, be = h * P2 * d, ga = h * P3 * d * d;
+            const double al2 = al * al;
+            // dz = d (1 + al/2 + (be + al^2)/6 + (ga + 4 al be + al^3)/24)
+            const double s4 = fma(al, fma(4.0, be, al2), ga);
+            const double corr = fma(s4, 1.0 / 24.0, fma(be + al2, 1.0 / 6.0, fma(al, 0.5, 1.0)));
+            const double zn = fma(d, corr, z);
+            if (fabs(al) <= PS_RELBW_ALPHA_OK) {
+                z = zn;
+                done = true;
+                break;
+            }
+            if (!(fabs(al) <= PS_RELBW_ALPHA_RETRY)) break;  // series useless (or NaN): generic solver
+            // rare: move (t, z) along consistently and evaluate again
+            t += atan((zn - z) / fma(z, zn, 1.0));
+            z = zn;
+            inv_zz1 = 1.0 / fma(z, z, 1.0);
+        }
+        if (!done) z = relbw_solve_generic(k, t_lo, t_hi, t0, target);
+    } else {
+        z = relbw_solve_generic(k, t_lo, t_hi, t0, target);
+    }
+    return clamp_mass(fma(k.c1, z, k.c0), lo, hi);
+}
+
+template <bool CONST_LIM>
+__device__ __forceinline__ double sample_mass(int kind, const SamplerConst& k, const double* lim, double lo, double hi,
+                                              double u) {
     switch (kind) {
-        case PS_KIND_GAUSS: return sample_gauss(m, w, lo, hi, u);
-        case PS_KIND_BW: return sample_cauchy(m, w, lo, hi, u);
-        default: return sample_relbw(m, w, lo, hi, u);
+        case PS_KIND_GAUSS: return sample_gauss<CONST_LIM>(k, lim, lo, hi, u);
+        case PS_KIND_BW: return sample_cauchy<CONST_LIM>(k, lim, lo, hi, u);
+        default: return sample_relbw<CONST_LIM>(k, lim, lo, hi, u);
     }
 }
 
