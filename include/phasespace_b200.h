@@ -128,11 +128,15 @@ int ps_unweight_index(const uint32_t* mask, const int64_t* tile_offsets, uint64_
  * tests/helpers/plotting.py:12-15): generates events [first_event, first_event + n_events) exactly as ps_generate
  * would, but instead of storing them accumulates, per particle slot s, weighted histograms (weight = w / w_max) of
  * px, py, pz on [p_lo, p_hi) and of E on [e_lo, e_hi), plus an unweighted histogram of w / w_max on [0, 1+1e-8).
+ *   w_cap expected upper bound of the normalised weights (1 is always safe; a tighter bound, e.g. a few times the
+ *         largest weight of a pilot sample, keeps more of a many-body decay's tiny weights on the fast fixed-point
+ *         path); weights outside [w_cap 2^-26, w_cap) are still accumulated correctly, only more slowly.
  *   hist  device double[(4 P + 1) * n_bins], caller-zeroed, ADDED to: row 4 s + k = coordinate k of slot s,
- *         last row = weights.  Sums are accumulated with fp64 atomics (order not reproducible to the last bit). */
+ *         last row = weights.  Accumulated per CTA in exact fixed point (ps_kernel.cuh); only the final per-CTA
+ *         fp64 adds into hist are order dependent. */
 int ps_histogram(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events, const double* boost_to,
-                 int64_t boost_rows, int32_t n_bins, double p_lo, double p_hi, double e_lo, double e_hi, double* hist,
-                 int32_t* err_flag, uint32_t flags, void* stream);
+                 int64_t boost_rows, int32_t n_bins, double p_lo, double p_hi, double e_lo, double e_hi, double w_cap,
+                 double* hist, int32_t* err_flag, uint32_t flags, void* stream);
 
 /* Stand-alone resonance sampler, the device implementation behind the callables of
  * fromdecay/mass_functions.py:31-38, 58-65, 89-100: out[i] ~ kind(mass, width) within

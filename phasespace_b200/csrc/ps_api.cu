@@ -824,25 +824,25 @@ extern "C" int ps_unweight_index(const uint32_t* mask, const int64_t* tile_offse
 namespace {
 struct PsHistParamsHost {  // must match psk::PsHistParams (ps_kernel.cuh)
     int n_bins;
-    int rep_log2;
+    int pad_;
     double p_lo, p_inv_width, e_lo, e_inv_width, w_inv_width;
+    double w_cap, fixed_scale;
     double* hist;
 };
 }  // namespace
 
 extern "C" int ps_histogram(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events,
                             const double* boost_to, int64_t boost_rows, int32_t n_bins, double p_lo, double p_hi,
-                            double e_lo, double e_hi, double* hist, int32_t* err_flag, uint32_t flags, void* stream) {
+                            double e_lo, double e_hi, double w_cap, double* hist, int32_t* err_flag, uint32_t flags,
+                            void* stream) {
     if (!tree || !hist) return fail(PS_E_INVALID, "null argument");
     if (tree->n_user > 0) return fail(PS_E_INVALID, "ps_histogram does not take user-mass trees");
     if (n_bins < 1 || !(p_hi > p_lo) || !(e_hi > e_lo)) return fail(PS_E_INVALID, "bad histogram binning");
-    size_t smem = (size_t)(4 * tree->n_particles + 1) * (size_t)n_bins * sizeof(double);
-    if (smem > 96 * 1024) return fail(PS_E_INVALID, "histograms need %zu bytes of shared memory per CTA (limit 96 KiB): use fewer bins", smem);
-    int rep_log2 = 0;  // interleaved copies per cell (PsHistParams): as many as fit in ~100 KiB, at most 8
-    while (rep_log2 < 3 && (smem << 1) <= 100 * 1024) {
-        smem <<= 1;
-        ++rep_log2;
-    }
+    if (!(w_cap > 0.0) || !std::isfinite(w_cap)) return fail(PS_E_INVALID, "w_cap must be a positive finite number");
+    // per cell: one fp64 accumulator and PS_HIST_LIMBS 32-bit limbs (ps_kernel.cuh: genbod_hist_body)
+    const size_t smem = (size_t)(4 * tree->n_particles + 1) * (size_t)n_bins * (sizeof(double) + PS_HIST_LIMBS * sizeof(uint32_t));
+    if (smem > 200 * 1024) return fail(PS_E_INVALID, "histograms need %zu bytes of shared memory per CTA (limit 200 KiB): use fewer bins", smem);
+    const double cap2 = std::exp2(std::ceil(std::log2(w_cap)));  // power of two >= w_cap: the scale below is exact
     PsParams p;
     int rc = fill_params(tree, p, seed, first_event, nullptr, n_events, boost_to, boost_rows, nullptr, nullptr, nullptr,
                          nullptr, nullptr, 0, nullptr, err_flag, flags | PS_GEN_NORMALIZE);
@@ -861,7 +861,8 @@ extern "C" int ps_histogram(const ps_tree* tree, uint64_t seed, uint64_t first_e
     }
     const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
     const int grid = (int)((long long)sms * per_sm < tiles ? (long long)sms * per_sm : tiles);
-    PsHistParamsHost h{n_bins, rep_log2, p_lo, n_bins / (p_hi - p_lo), e_lo, n_bins / (e_hi - e_lo), n_bins / (1.0 + 1e-8), hist};
+    PsHistParamsHost h{n_bins, 0, p_lo, n_bins / (p_hi - p_lo), e_lo, n_bins / (e_hi - e_lo), n_bins / (1.0 + 1e-8),
+                       cap2, std::exp2((double)(PS_HIST_LIMBS * PS_HIST_LIMB_BITS)) / cap2, hist};
     void* args[] = {&p, &h};
     PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, smem, (cudaStream_t)stream));
     g_launches.fetch_add(1);

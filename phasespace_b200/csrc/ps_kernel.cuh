@@ -824,32 +824,76 @@ __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS)
 // The consumer of the reference's own physics tests (tests/test_physics.py:96-107): a weighted histogram of every
 // coordinate of every particle (momentum components on [p_lo, p_hi), energies on [e_lo, e_hi), weight = the
 // normalised event weight) plus an unweighted histogram of the weights on [0, 1 + 1e-8).  Events are generated
-// exactly as by genbod_kernel but never stored: each CTA accumulates into shared memory (fp64 shared atomics)
-// and adds its histograms to the global ones once at the end, so the kernel is bound by the fp64 pipe, not HBM.
-// fp64 shared-memory atomics are compare-and-swap loops (ATOMS.CAST.SPIN.64) that retry on every collision, so each
-// CTA keeps 2^rep_log2 interleaved copies of every cell and lane l adds to copy l mod 2^rep_log2: lanes of one
-// warp that fall into the same bin mostly hit different copies (adjacent addresses, different banks).
+// exactly as by genbod_kernel but never stored.
+//
+// Accumulation: shared-memory atomics exist natively only for 32-bit integers on sm_100a (fp64 and 64-bit integer
+// adds compile to compare-and-swap retry loops, ATOMS.CAST.SPIN.64, which made the first version of this kernel
+// slower than generating and storing the events).  So the weight is turned into a 60-bit fixed-point integer once
+// per event (w * 2^57, weights below 8) and added as three 20-bit limbs with native ATOMS.ADD; a 32-bit cell takes
+// 4096 such adds before it can overflow, so every PS_HIST_FOLD_TILES tiles the CTA folds the limbs into fp64
+// accumulators (one owner thread per cell, no atomics) and clears them.  Integer sums are exact and order
+// independent; the only roundings are the fixed-point conversion (2^-57 absolute) and one per fold.
 struct PsHistParams {
     int n_bins;
-    int rep_log2;
+    int pad_;
     double p_lo, p_inv_width, e_lo, e_inv_width, w_inv_width;
+    double w_cap;        // weights in [w_cap 2^-PS_HIST_MIN_EXP, w_cap) take the fixed-point path (a power of two)
+    double fixed_scale;  // 2^(PS_HIST_LIMBS * PS_HIST_LIMB_BITS) / w_cap
     double* hist;  // (4 P + 1, n_bins): rows px,py,pz,E of slot 0, ... , then the weight histogram
 };
+// a 32-bit cell takes 2^(32 - LIMB_BITS) adds of < 2^LIMB_BITS each; one tile adds at most PS_BLOCK per cell
+#define PS_HIST_FOLD_TILES ((1 << (32 - PS_HIST_LIMB_BITS)) / PS_BLOCK)
+// weights below w_cap * 2^-PS_HIST_MIN_EXP would lose relative precision in fixed point: they take the fp64 path
+#define PS_HIST_MIN_EXP (PS_HIST_LIMBS * PS_HIST_LIMB_BITS - 34)
 
-template <class C, int S>
-__device__ __forceinline__ void hist_particle(const C& c, const PsHistParams& h, double* sh, int copy, double w) {
+// bin of one coordinate, or an out-of-range index (as unsigned) if v is outside [lo, lo + n_bins / inv_width)
+__device__ __forceinline__ unsigned int hist_bin(double v, double lo, double inv_width) {
+    return (unsigned int)__double2int_rd((v - lo) * inv_width);  // saturates: far out-of-range values stay out of range
+}
+
+// shared layout: double acc[n_cells] | unsigned limbs[n_cells][PS_HIST_LIMBS]   (n_cells = (4 P + 1) n_bins)
+// FAST: the event's weight as fixed-point limbs, native 32-bit atomics, no branches; else fp64 compare-and-swap loops.
+template <bool FAST, class C, int S>
+__device__ __forceinline__ void hist_particle(const C& c, const PsHistParams& h, double* acc, unsigned int* limbs,
+                                              const unsigned int (&l)[PS_HIST_LIMBS], double w) {
     const double v[4] = {c.px[S], c.py[S], c.pz[S], c.en[S]};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const double t = (v[k] - (k == 3 ? h.e_lo : h.p_lo)) * (k == 3 ? h.e_inv_width : h.p_inv_width);
-        const int bin = (int)floor(t);
-        if (t >= 0.0 && bin < h.n_bins) atomicAdd(&sh[(((4 * S + k) * h.n_bins + bin) << h.rep_log2) + copy], w);
+        const unsigned int bin = hist_bin(v[k], k == 3 ? h.e_lo : h.p_lo, k == 3 ? h.e_inv_width : h.p_inv_width);
+        if (bin < (unsigned int)h.n_bins) {
+            const unsigned int cell = (4 * S + k) * h.n_bins + bin;
+            if constexpr (FAST) {
+#pragma unroll
+                for (int j = 0; j < PS_HIST_LIMBS; ++j) atomicAdd(limbs + cell * PS_HIST_LIMBS + j, l[j]);
+            } else {
+                atomicAdd(&acc[cell], w);
+            }
+        }
     }
 }
-template <class C, int... S>
-__device__ __forceinline__ void hist_particles(const C& c, const PsHistParams& h, double* sh, int copy, double w,
-                                               Seq<S...>) {
-    (hist_particle<C, S>(c, h, sh, copy, w), ...);
+template <bool FAST, class C, int... S>
+__device__ __forceinline__ void hist_particles(const C& c, const PsHistParams& h, double* acc, unsigned int* limbs,
+                                               const unsigned int (&l)[PS_HIST_LIMBS], double w, Seq<S...>) {
+    (hist_particle<FAST, C, S>(c, h, acc, limbs, l, w), ...);
+}
+
+// value of the limbs of one cell (each limb sum is < 2^32, exact in fp64; the combination rounds once), then cleared
+__device__ __forceinline__ double hist_take_cell(unsigned int* q) {
+    double v = 0.0;
+#pragma unroll
+    for (int j = PS_HIST_LIMBS - 1; j >= 0; --j) {
+        v = fma(v, (double)(1u << PS_HIST_LIMB_BITS), (double)q[j]);
+        q[j] = 0u;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void hist_fold(const PsHistParams& h, double* acc, unsigned int* limbs, int n_cells) {
+    __syncthreads();
+    const double inv_scale = 1.0 / h.fixed_scale;
+    for (int k = threadIdx.x; k < n_cells; k += PS_BLOCK)
+        acc[k] = fma(hist_take_cell(limbs + k * PS_HIST_LIMBS), inv_scale, acc[k]);
+    __syncthreads();
 }
 
 template <class Tree, bool BOOST>
@@ -857,11 +901,15 @@ __device__ __forceinline__ void genbod_hist_body(const PsParams& prm, const PsHi
     constexpr int P = Tree::n_below;
     extern __shared__ double sh[];
     const int n_cells = (4 * P + 1) * h.n_bins;
-    const int copy = threadIdx.x & ((1 << h.rep_log2) - 1);
-    for (int k = threadIdx.x; k < (n_cells << h.rep_log2); k += PS_BLOCK) sh[k] = 0.0;
+    double* acc = sh;
+    unsigned int* limbs = reinterpret_cast<unsigned int*>(sh + n_cells);
+    for (int k = threadIdx.x; k < n_cells; k += PS_BLOCK) acc[k] = 0.0;
+    for (int k = threadIdx.x; k < n_cells * PS_HIST_LIMBS; k += PS_BLOCK) limbs[k] = 0u;
     __syncthreads();
     bool bad_any = false;
     const long long n = prm.n_events;
+    const double w_min = h.w_cap * (1.0 / (double)(1ull << PS_HIST_MIN_EXP));
+    int since_fold = 0;
     for (long long tile = blockIdx.x; tile * PS_BLOCK < n; tile += gridDim.x) {
         const long long i = tile * PS_BLOCK + threadIdx.x;
         if (i < n) {
@@ -880,17 +928,32 @@ __device__ __forceinline__ void genbod_hist_body(const PsParams& prm, const PsHi
 #else
             const double w_norm = w * inv_w_max;
 #endif
-            hist_particles(c, h, sh, copy, w_norm, MakeSeq<P>{});
-            const int wb = (int)floor(w_norm * h.w_inv_width);
-            if (w_norm >= 0.0 && wb < h.n_bins) atomicAdd(&sh[((4 * P * h.n_bins + wb) << h.rep_log2) + copy], 1.0);
+            bool fixed_ok = w_norm >= w_min && w_norm < h.w_cap;
+            const unsigned long long fx = fixed_ok ? (unsigned long long)__double2ll_rn(w_norm * h.fixed_scale) : 0ull;
+            unsigned int l[PS_HIST_LIMBS];
+#pragma unroll
+            for (int j = 0; j < PS_HIST_LIMBS; ++j)
+                l[j] = (unsigned int)(fx >> (j * PS_HIST_LIMB_BITS)) & ((1u << PS_HIST_LIMB_BITS) - 1u);
+            fixed_ok = fixed_ok && (fx >> (PS_HIST_LIMBS * PS_HIST_LIMB_BITS)) == 0ull;  // rounded up to w_cap itself
+            if (fixed_ok)
+                hist_particles<true>(c, h, acc, limbs, l, w_norm, MakeSeq<P>{});
+            else  // far outside the expected range of weights (rare): fp64 atomics
+                hist_particles<false>(c, h, acc, limbs, l, w_norm, MakeSeq<P>{});
+            const unsigned int wb = hist_bin(w_norm, 0.0, h.w_inv_width);
+            if (wb < (unsigned int)h.n_bins)  // a count: limb 0 of the weight row
+                atomicAdd(limbs + (4 * P * h.n_bins + wb) * PS_HIST_LIMBS, 1u);
             bad_any |= c.bad;
+        }
+        if (++since_fold == PS_HIST_FOLD_TILES) {
+            hist_fold(h, acc, limbs, n_cells);
+            since_fold = 0;
         }
     }
     if (bad_any) *prm.err_flag = PS_ERR_FORBIDDEN;
-    __syncthreads();
+    hist_fold(h, acc, limbs, n_cells);
     for (int k = threadIdx.x; k < n_cells; k += PS_BLOCK) {
-        double v = 0.0;
-        for (int r = 0; r < (1 << h.rep_log2); ++r) v += sh[(k << h.rep_log2) + r];
+        // the weight row holds counts in units of 1/fixed_scale (a power of two: exact)
+        const double v = k >= 4 * P * h.n_bins ? acc[k] * h.fixed_scale : acc[k];
         if (v != 0.0) atomicAdd(&h.hist[k], v);
     }
 }

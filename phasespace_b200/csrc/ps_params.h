@@ -16,6 +16,14 @@
 #define PS_KIND_RELBW 3 /* relativistic Breit-Wigner density in the mass (mass_functions.py:70-102) */
 #define PS_KIND_USER 4  /* per-event masses supplied by the caller (arbitrary Python callables) */
 
+/* fused histograms (ps_kernel.cuh: genbod_hist_body): fixed-point weight = PS_HIST_LIMBS limbs of PS_HIST_LIMB_BITS bits */
+#ifndef PS_HIST_LIMBS
+#define PS_HIST_LIMBS 3
+#endif
+#ifndef PS_HIST_LIMB_BITS
+#define PS_HIST_LIMB_BITS 20
+#endif
+
 #define PS_ERR_FORBIDDEN 1 /* available_mass < 0 or NaN: "Forbidden decay" (phasespace.py:357-363) */
 
 typedef struct PsParams {

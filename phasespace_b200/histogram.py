@@ -20,13 +20,17 @@ from .random import SeedLike, get_rng
 
 def generate_histograms(decay, n_events: int, seed: SeedLike = None, *, bins: int = 100, p_range=(-3000.0, 3000.0),
                         e_range=(0.0, 3000.0), boost_to=None, normalize: bool = True, chunk_events: int = 1 << 30,
-                        exact: bool = False):
+                        exact: bool = False, w_cap: float | None = None):
     """Weighted histograms of ``decay.generate(n_events, seed=seed)`` without materialising the events.
 
     Returns ``(particle_histos, weight_histo)``: ``particle_histos[name]`` is a ``(4, bins)`` CUDA tensor (rows px, py,
     pz, E; each event enters with its normalised weight) and ``weight_histo`` a ``(bins,)`` tensor of event counts in
     bins of the normalised weight on ``[0, 1 + 1e-8)``.  With ``normalize`` every histogram is divided by its sum,
     like the reference's ``make_norm_histo`` (tests/helpers/plotting.py:12-15).
+
+    ``w_cap`` is the expected upper bound of the normalised weights: weights within 26 binary orders of magnitude
+    below it are accumulated in exact fixed point with native shared-memory atomics, the others (still correctly)
+    with slower fp64 atomics.  By default it is four times the largest weight of a 32768-event pilot sample.
     """
     device = _device()
     n = int(n_events)
@@ -48,13 +52,22 @@ def generate_histograms(decay, n_events: int, seed: SeedLike = None, *, bins: in
                              f"of {tuple(boost_to.shape)}")
     stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     flags = _lib.PS_GEN_EXACT if exact else 0
+    if w_cap is None and n > 0:  # pilot: the first events of the same stream
+        m = min(n, 32768)
+        stats = torch.zeros((4,), dtype=torch.float64, device=device)
+        pilot_boost = boost_to if boost_rows <= 1 else boost_to[:m]
+        compiled.launch(m, rng.seed, first, boost_to=pilot_boost, exact=exact, stats=stats, err=err)
+        w_cap = 4.0 * float(stats[0].item())
+        err.zero_()  # a forbidden pilot event is reported by the real pass
+    if not w_cap or not (w_cap > 0.0) or w_cap != w_cap or w_cap == float("inf"):
+        w_cap = 1.0
     done = 0
     while done < n:  # chunking only bounds the launch size; the histograms accumulate
         m = min(chunk_events, n - done)
         b = boost_to[done:done + m] if boost_rows == n and n != 1 else boost_to
         _lib.check(_lib.lib.ps_histogram(
             compiled.handle, rng.seed, first + done, m, _ptr(b), (m if boost_rows == n and n != 1 else boost_rows),
-            int(bins), float(p_range[0]), float(p_range[1]), float(e_range[0]), float(e_range[1]), _ptr(hist),
+            int(bins), float(p_range[0]), float(p_range[1]), float(e_range[0]), float(e_range[1]), float(w_cap), _ptr(hist),
             _ptr(err), flags, stream))
         done += m
     if n > 0 and (compiled.has_resonances or boost_to is not None) and int(err.item()):
