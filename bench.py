@@ -294,6 +294,29 @@ def run_b200(args, rank, local_rank, world):
                       "d2h_bytes_per_step": 8, "steps": dev_steps, "mean_w": mean_w,
                       "api": "GenParticle.generate (allocates outputs) + weights.mean().item(); events stay in HBM"}
         del w_dev, parts_dev
+    # ---- supplementary: the histogram consumer of the reference's physics tests, fused into the generator
+    # (generate_histograms): per step only 13 x 100 doubles cross PCIe
+    e2e_hist = None
+    if not args.no_e2e:
+        from phasespace_b200.histogram import generate_histograms
+
+        generate_histograms(decay, n, seed=args.seed, w_cap=1.0)
+        barrier()
+        hist_steps = max(1, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for k in range(hist_steps):
+            hp, hw = generate_histograms(decay, n, seed=args.seed + k, w_cap=1.0)
+            hw_host = hw.cpu()
+            hp_host = {name: h.cpu() for name, h in hp.items()}
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_hist = {"value": world * n * hist_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 8 * 100 * (4 * N_BODY + 1), "steps": hist_steps,
+                    "sum_weight_histogram": float(hw_host.sum()),
+                    "api": "histogram.generate_histograms -> ps_histogram (events binned in shared memory, never stored) "
+                           "+ the normalised histograms copied to the host"}
     sampler.stop()
 
     if rank == 0:
@@ -312,6 +335,18 @@ def run_b200(args, rank, local_rank, world):
         except Exception:
             pass
         achieved = BYTES_PER_EVENT * n / (kernel_ms * 1e-3) / 1e9
+        # the other bound of the north star: fp64 instructions at the measured pipe peak (profiles/fp64_pipe.json,
+        # tools/fp64_bench.cu; instruction count per event from the ncu pass in profiles/)
+        fp64 = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "fp64_pipe.json")) as fh:
+                f = json.load(fh)
+            bound = f["peak_fp64_inst_per_s"] / f["fp64_inst_per_event"]["flat_3body"]
+            fp64 = {"fp64_inst_per_event": f["fp64_inst_per_event"]["flat_3body"], "peak_fp64_inst_per_s": f["peak_fp64_inst_per_s"],
+                    "bound_events_per_s": bound, "frac": n / (kernel_ms * 1e-3) / bound,
+                    "note": "HBM is the binding roofline for the 3-body decay; fp64 pipe peak measured with tools/fp64_bench.cu"}
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": world * n * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -319,13 +354,15 @@ def run_b200(args, rank, local_rank, world):
             "config": _config(n, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": BYTES_PER_EVENT * n, "kernel_ms": kernel_ms},
+                         "algorithmic_bytes_per_launch": BYTES_PER_EVENT * n, "kernel_ms": kernel_ms, "fp64_bound": fp64},
             "clocks": clocks, "gpu_launches": int(launches), "global_stats": global_stats,
         }
         if e2e is not None:
             line["e2e"] = e2e
         if e2e_device is not None:
             line["e2e_device_consumer"] = e2e_device
+        if e2e_hist is not None:
+            line["e2e_histogram_consumer"] = e2e_hist
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
