@@ -194,3 +194,47 @@ def test_forbidden_decay_raises():
     boost = np.array([[0.0, 0.0, 100.0, 250.0]])
     with pytest.raises(ps.ForbiddenDecayError):
         ps.nbody_decay(D.B0_MASS, [139.57018] * 3).generate(10, boost_to=boost)
+
+
+def _random_tree(rng, depth=0, name="top"):
+    """A random decay tree description: fan-out 2-4, depth <= 3, at most one sampled resonance per sibling group
+    (a second one could be squeezed out by the Cauchy tail of the first: SURVEY.md quirk 4), fixed-mass
+    intermediates otherwise.  Returns (desc, sum of leaf masses)."""
+    n_children = int(rng.integers(2, 5 if depth < 2 else 3))
+    children, leaf_sum, sampled_used = [], 0.0, False
+    for j in range(n_children):
+        cname = f"{name}_{j}"
+        if depth < 2 and rng.random() < 0.45:
+            sub, sub_leaves = _random_tree(rng, depth + 1, cname)
+            kind = "fixed" if sampled_used else str(rng.choice(["fixed", "gauss", "bw", "relbw"]))
+            sampled_used |= kind != "fixed"
+            mass = sub_leaves * float(rng.uniform(1.3, 2.0))
+            width = 0.0 if kind == "fixed" else mass * float(rng.uniform(0.005, 0.08))
+            children.append((cname, mass, kind, width, sub[4]))
+            leaf_sum += mass if kind == "fixed" else sub_leaves
+        else:
+            mass = float(rng.choice([0.0, 0.511, 105.66, 139.57018, 493.677, 938.272]))
+            children.append((cname, mass, "fixed", 0.0, []))
+            leaf_sum += mass
+    return (name, 0.0, "fixed", 0.0, children), leaf_sum
+
+
+def _node_floor(desc):
+    """Smallest mass the node can take: its own mass if fixed, else the sum of the floors below it."""
+    return desc[1] if desc[2] == "fixed" and desc[1] > 0 else sum(_node_floor(c) for c in desc[4])
+
+
+@pytest.mark.parametrize("tree_seed", [1, 2, 3, 4, 5])
+def test_random_trees_jit(tree_seed):
+    """Randomly shaped trees (none of them compiled ahead of time) through NVRTC, in-kernel Philox, against the oracle."""
+    rng = np.random.default_rng(1000 + tree_seed)
+    desc, _ = _random_tree(rng)
+    # room for the widest resonance: the top mass well above the sum of the pole masses of its children
+    top_mass = 3.0 * sum(c[1] if c[4] else _node_floor(c) for c in desc[4]) + 1000.0
+    desc = (desc[0], top_mass, "fixed", 0.0, desc[4])
+    # Tolerance: the reference (and the oracle) re-derive the mass of every decaying particle as sqrt(E^2 - p^2) of
+    # its boosted 4-vector (SURVEY.md quirk 2), which loses eps * gamma^2 per level; two or three levels of light
+    # intermediates push the weight differences to ~1e-10.  Far Cauchy tails also land within ~1e-4 of a threshold
+    # now and then (see _check_weights).
+    _compare(desc, 4000, exact=False, use_rng=True, tol=3e-10, loose=1e-6)
+    _compare(desc, 500, exact=True, use_rng=False, tol=3e-10, loose=1e-6)
