@@ -149,6 +149,18 @@ int ps_lorentz_boost(const double* vectors, const double* boost, int64_t boost_r
                      int64_t n, double* out, void* stream);
 int ps_mass(const double* vectors, int64_t n, double* out, void* stream);
 
+/* FONLL-style boost_to generator, the input-side caller of the path in the reference's tests
+ * (tests/helpers/rapidsim.py:23-51, generate_fonll): per event pT and eta are drawn from binned spectra (bin centres
+ * with probabilities, numpy.random.choice semantics = inverse CDF with side="right"), phi uniformly in [0, 2 pi);
+ * out row i = [pT cos phi, pT sin phi, pT sinh eta, sqrt(p^2 + mass^2)] with pT = pt_scale * |centre| -- directly usable
+ * as boost_to.  Three Philox draws per event (stream 4, columns 0-2).
+ *   pt_centers, pt_cdf   device double[n_pt]: bin centres and the normalised cumulative sum of the bin contents
+ *   eta_centers, eta_cdf device double[n_eta]
+ *   out                  device double[n_events * 4], 32-byte aligned */
+int ps_fonll_boost(const double* pt_centers, const double* pt_cdf, int32_t n_pt, const double* eta_centers,
+                   const double* eta_cdf, int32_t n_eta, double mass, double pt_scale, uint64_t seed, uint64_t first_event,
+                   int64_t n_events, double* out, void* stream);
+
 const char* ps_last_error(void);
 int32_t ps_abi_version(void);
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */

@@ -405,3 +405,30 @@ def generate(part: Part, n_events, draws, boost_to=None, normalize_weights=True,
     if normalize_weights:
         return weights / weights_max, parts
     return weights, weights_max, parts
+
+
+# ----------------------------------------------------------------------------- FONLL-style boosts
+def generate_fonll(mass, pt_centers, pt_values, eta_centers, eta_values, draws, pt_scale=1000.0):
+    """``tests/helpers/rapidsim.py:23-51`` (``generate_fonll``) with the random numbers as an argument.
+
+    ``draws`` is ``(n_events, 3)``: the uniforms behind ``np.random.choice`` for pT, for eta, and the one scaled to
+    phi.  ``np.random.choice(a, p=p)`` is ``a[cumsum(p).searchsorted(u, side="right")]`` with the cumulative sum
+    renormalised to end at 1.  Returns ``(n_events, 4)`` rows ``[px, py, pz, E]`` (the reference stacks them as
+    ``(4, n_events)`` and transposes at the call site, tests/test_physics.py:190-191).
+    """
+    def choice(centers, values, u):
+        p = np.asarray(values, dtype=np.float64) / np.sum(values)
+        cdf = np.cumsum(p)
+        cdf /= cdf[-1]
+        idx = np.minimum(cdf.searchsorted(u, side="right"), len(cdf) - 1)
+        return np.asarray(centers, dtype=np.float64)[idx]
+
+    draws = np.asarray(draws, dtype=np.float64)
+    pt_rand = pt_scale * np.abs(choice(pt_centers, pt_values, draws[:, 0]))
+    eta_rand = choice(eta_centers, eta_values, draws[:, 1])
+    phi_rand = draws[:, 2] * (2 * np.pi)
+    px = pt_rand * np.cos(phi_rand)
+    py = pt_rand * np.sin(phi_rand)
+    pz = pt_rand * np.sinh(eta_rand)
+    e = np.sqrt(px * px + py * py + pz * pz + mass * mass)
+    return np.stack([px, py, pz, e], axis=1)

@@ -17,7 +17,7 @@ _LAZY = {
     "GenParticle": ".phasespace", "nbody_decay": ".phasespace", "to_vectors": ".phasespace",
     "ForbiddenDecayError": ".phasespace", "CompiledDecay": ".phasespace",
 }
-_SUBMODULES = {"random", "kinematics", "phasespace", "fromdecay", "sharding", "unweight", "histogram", "_lib", "build"}
+_SUBMODULES = {"random", "kinematics", "phasespace", "fromdecay", "sharding", "unweight", "histogram", "boost", "_lib", "build"}
 
 
 def __getattr__(name):

@@ -55,6 +55,7 @@ def _load():
         "ps_unweight_scan": (c.c_int, [vp, i64, vp, vp, vp]),
         "ps_unweight_index": (c.c_int, [vp, vp, u64, i64, vp, vp]),
         "ps_histogram": (c.c_int, [vp, u64, u64, i64, vp, i64, i32, dbl, dbl, dbl, dbl, dbl, vp, vp, u32, vp]),
+        "ps_fonll_boost": (c.c_int, [vp, vp, i32, vp, vp, i32, dbl, dbl, u64, u64, i64, vp, vp]),
         "ps_sample_mass": (c.c_int, [i32, dbl, dbl, vp, vp, i64, u64, u64, vp, vp]),
         "ps_lorentz_boost": (c.c_int, [vp, vp, i64, i32, i64, vp, vp]),
         "ps_mass": (c.c_int, [vp, i64, vp, vp]),

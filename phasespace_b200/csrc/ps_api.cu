@@ -919,6 +919,39 @@ __global__ void __launch_bounds__(PS_BLOCK) mass_kernel(const double* v, long lo
     }
 }
 
+// numpy.random.choice(centres, p=probabilities): cdf.searchsorted(u, side="right")
+__device__ __forceinline__ int choice_index(const double* cdf, int n, double u) {
+    int lo = 0, hi = n;  // first index with cdf[index] > u
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cdf[mid] > u) hi = mid; else lo = mid + 1;
+    }
+    return lo < n ? lo : n - 1;
+}
+
+// tests/helpers/rapidsim.py:23-51
+__global__ void __launch_bounds__(PS_BLOCK) fonll_boost_kernel(const double* pt_centers, const double* pt_cdf, int n_pt,
+                                                               const double* eta_centers, const double* eta_cdf, int n_eta,
+                                                               double mass, double pt_scale, unsigned long long seed,
+                                                               unsigned long long first_event, long long n, double* out) {
+    for (long long i = (long long)blockIdx.x * PS_BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * PS_BLOCK) {
+        const unsigned long long ev = first_event + (unsigned long long)i;
+        const double u_pt = psk::philox_uniform_col<0>(seed, ev, 4u), u_eta = psk::philox_uniform_col<1>(seed, ev, 4u);
+        const double u_phi = psk::philox_uniform_col<2>(seed, ev, 4u);
+        const double pt = __dmul_rn(pt_scale, fabs(pt_centers[choice_index(pt_cdf, n_pt, u_pt)]));
+        const double eta = eta_centers[choice_index(eta_cdf, n_eta, u_eta)];
+        double s, c;
+        sincos(__dmul_rn(u_phi, 2.0 * 3.141592653589793), &s, &c);
+        const double px = __dmul_rn(pt, c), py = __dmul_rn(pt, s), pz = __dmul_rn(pt, sinh(eta));
+        double e2 = __dmul_rn(px, px);
+        e2 = __dadd_rn(e2, __dmul_rn(py, py));
+        e2 = __dadd_rn(e2, __dmul_rn(pz, pz));
+        e2 = __dadd_rn(e2, __dmul_rn(mass, mass));
+        reinterpret_cast<double2*>(out + 4 * i)[0] = make_double2(px, py);
+        reinterpret_cast<double2*>(out + 4 * i)[1] = make_double2(pz, sqrt(e2));
+    }
+}
+
 int small_grid(long long n) {
     long long g = (n + PS_BLOCK - 1) / PS_BLOCK;
     if (g > 148 * 16) g = 148 * 16;
@@ -937,6 +970,19 @@ extern "C" int ps_sample_mass(int32_t kind, double mass, double width, const dou
     host_sampler_constants(kind, mass, width, sc);
     const psk::SamplerConst k{mass, width, sc[0], sc[1], sc[2], sc[3], sc[4]};
     sample_mass_kernel<<<small_grid(n_events), PS_BLOCK, 0, (cudaStream_t)stream>>>(kind, k, min_mass, max_mass, n_events, seed, first_event, out);
+    PS_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+extern "C" int ps_fonll_boost(const double* pt_centers, const double* pt_cdf, int32_t n_pt, const double* eta_centers,
+                              const double* eta_cdf, int32_t n_eta, double mass, double pt_scale, uint64_t seed,
+                              uint64_t first_event, int64_t n_events, double* out, void* stream) {
+    if (!pt_centers || !pt_cdf || !eta_centers || !eta_cdf || !out || n_events < 0) return fail(PS_E_INVALID, "null argument");
+    if (n_pt < 1 || n_eta < 1) return fail(PS_E_INVALID, "ps_fonll_boost: empty spectrum");
+    if (!aligned32(out)) return fail(PS_E_INVALID, "ps_fonll_boost: out must be 32-byte aligned");
+    if (n_events == 0) return 0;
+    fonll_boost_kernel<<<small_grid(n_events), PS_BLOCK, 0, (cudaStream_t)stream>>>(pt_centers, pt_cdf, n_pt, eta_centers, eta_cdf, n_eta, mass, pt_scale, seed, first_event, n_events, out);
     PS_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     return 0;

@@ -62,6 +62,24 @@ __device__ __forceinline__ double uniform_from_bits(unsigned int lo, unsigned in
     return fma(__hiloint2double((int)((hi & 0x7FFFFu) | 0x3FF00000u), (int)lo), 2.0, -2.0);
 }
 
+// uniform number COL of an event in any stream (same bit layout as Ctx::next in ps_kernel.cuh, blocks recomputed
+// per call: for the small helper kernels that draw two or three numbers per event)
+template <int COL>
+__device__ __forceinline__ double philox_uniform_col(unsigned long long seed, unsigned long long event, unsigned int stream) {
+    constexpr int bit0 = PS_UNIFORM_BITS * COL;
+    constexpr int FB = bit0 / 128, LB = (bit0 + PS_UNIFORM_BITS - 1) / 128;
+    constexpr int o = bit0 - 128 * FB, i = o / 32, sh = o % 32;
+    const Philox4 a = philox4x32_10(seed, event, FB, stream);
+    unsigned int x[8] = {a.w[0], a.w[1], a.w[2], a.w[3], 0u, 0u, 0u, 0u};
+    if constexpr (LB > FB) {
+        const Philox4 b = philox4x32_10(seed, event, LB, stream);
+        x[4] = b.w[0], x[5] = b.w[1], x[6] = b.w[2], x[7] = b.w[3];
+    }
+    const unsigned int lo = sh ? __funnelshift_r(x[i], x[i + 1], sh) : x[i];
+    const unsigned int hi = sh ? __funnelshift_r(x[i + 1], x[i + 2], sh) : x[i + 1];
+    return uniform_from_bits(lo, hi);
+}
+
 // first uniform of block 0 of a stream (acceptance draws, stand-alone samplers)
 __device__ __forceinline__ double philox_uniform0(unsigned long long seed, unsigned long long event, unsigned int stream) {
     const Philox4 r = philox4x32_10(seed, event, 0u, stream);

@@ -248,3 +248,42 @@ def test_launch_is_cuda_graph_capturable():
     w, _, p, _ = comp.launch(3 * n, 5)
     assert torch.equal(torch.cat([o["weights"] for o in outs]), w)
     assert torch.equal(torch.cat([o["particles"] for o in outs], dim=1), p)
+
+
+def test_fonll_boost_generator():
+    """generate_fonll (the reference tests' boost_to source, tests/helpers/rapidsim.py:23-51) on the device: equal to
+    the numpy restatement fed the same Philox draws, usable as boost_to, independent of how the range is split."""
+    from oracle import genbod_numpy as orc
+    from oracle.philox import uniform_table
+    from phasespace_b200.boost import generate_fonll
+    from phasespace_b200.random import Generator
+
+    pt_edges = np.linspace(0.0, 40.0, 81)
+    pt_centers = pt_edges[:-1] + 0.25
+    pt_values = np.exp(-pt_centers / 5.0) * pt_centers
+    eta_centers = np.linspace(1.9, 5.1, 33)
+    eta_values = np.exp(-0.5 * ((eta_centers - 3.2) / 0.9) ** 2)
+    n, seed = 100_003, 17
+    got = generate_fonll(B0_MASS, (pt_edges, pt_values), (eta_centers, eta_values), n, seed=seed)
+    assert tuple(got.shape) == (n, 4) and got.is_cuda
+    ref = orc.generate_fonll(B0_MASS, pt_centers, pt_values, eta_centers, eta_values, uniform_table(seed, 0, n, 3, stream=4))
+    scale = ref[:, 3].max()
+    assert np.max(np.abs(_np(got) - ref)) / scale < 1e-14
+    # the masses of the rows are the requested one; the spectrum is the requested one
+    m = np.sqrt(ref[:, 3] ** 2 - (ref[:, :3] ** 2).sum(1))
+    np.testing.assert_allclose(m, B0_MASS, rtol=1e-9)
+    pt = np.hypot(_np(got)[:, 0], _np(got)[:, 1]) / 1000.0
+    counts = np.histogram(pt, bins=pt_edges)[0] / n
+    assert np.max(np.abs(counts - pt_values / pt_values.sum())) < 5e-3
+    # one generator, two consecutive calls == one call (draws are keyed on the event index)
+    g = Generator(seed)
+    a = generate_fonll(B0_MASS, (pt_edges, pt_values), (eta_centers, eta_values), 60_000, seed=g)
+    b = generate_fonll(B0_MASS, (pt_edges, pt_values), (eta_centers, eta_values), n - 60_000, seed=g)
+    assert torch.equal(torch.cat([a, b]), got)
+    # as boost_to
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    w, parts = decay.generate(n, boost_to=got, seed=3)
+    total = sum(parts.values())
+    assert float((total - got).abs().max()) / scale < 1e-12
+    with pytest.raises(ValueError):
+        generate_fonll(B0_MASS, (pt_edges, pt_values[:-1]), (eta_centers, eta_values), 10)

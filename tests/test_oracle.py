@@ -217,3 +217,24 @@ def test_mass_samplers_follow_their_densities(kind, m, width, lo, hi):
         cum /= cum[-1]
         cdf = lambda v: np.interp(v, grid, cum)  # noqa: E731
     assert stats.kstest(x, cdf)[1] > 1e-3
+
+
+def test_fonll_oracle_is_numpy_choice():
+    """oracle.generate_fonll restates tests/helpers/rapidsim.py:23-51: fed the uniforms numpy's RandomState consumes,
+    it reproduces np.random.choice / np.random.uniform exactly."""
+    pt_edges = np.linspace(0.0, 40.0, 81)
+    pt_centers = pt_edges[:-1] + 0.25
+    pt_values = np.exp(-pt_centers / 5.0) * pt_centers
+    eta_centers = np.linspace(1.9, 5.1, 33)
+    eta_values = np.exp(-0.5 * ((eta_centers - 3.2) / 0.9) ** 2)
+    n, mass = 5000, 5279.58
+    rs = np.random.RandomState(7)
+    pt_rand = 1000 * np.abs(rs.choice(pt_centers, size=n, p=pt_values / np.sum(pt_values)))
+    eta_rand = rs.choice(eta_centers, size=n, p=eta_values / np.sum(eta_values))
+    phi_rand = rs.uniform(0, 2 * np.pi, size=n)
+    px, py, pz = pt_rand * np.cos(phi_rand), pt_rand * np.sin(phi_rand), pt_rand * np.sinh(eta_rand)
+    ref = np.stack([px, py, pz, np.sqrt(px * px + py * py + pz * pz + mass * mass)])
+    rs = np.random.RandomState(7)
+    draws = np.stack([rs.random_sample(n), rs.random_sample(n), rs.random_sample(n)], axis=1)
+    got = orc.generate_fonll(mass, pt_centers, pt_values, eta_centers, eta_values, draws)
+    np.testing.assert_array_equal(got, ref.transpose())
