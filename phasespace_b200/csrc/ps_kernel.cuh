@@ -85,10 +85,38 @@ struct Pt {
     }
 };
 
+// ------------------------------------------------------------------ products of two-body momenta
+// Fast variant: the maximum weight of a tree is a product of two-body momenta sqrt(x_i)/(2 a_i) over all decaying
+// nodes; only its reciprocal is needed to normalise the weight, so the factors are multiplied up first --
+// prod(2 a_i) * rsqrt(prod x_i) -- with one reciprocal square root per four factors (x_i ~ M^4: four of them stay
+// far from overflow for any mass scale) instead of a square root and a reciprocal per factor.
+struct WmaxAcc {
+    double rs = 1.0, px = 1.0, pe = 1.0;
+    int cnt = 0, n = 0;
+    __device__ __forceinline__ void add(double x, double two_a) {
+        px = cnt == 0 ? x : px * x;
+        pe = n == 0 ? two_a : pe * two_a;
+        ++n;
+        if (++cnt == 4) flush();
+    }
+    __device__ __forceinline__ void flush() {
+        if (cnt) rs = rs * rsqrt_pos(px);
+        cnt = 0;
+    }
+    __device__ __forceinline__ double inverse() {  // 1 / w_max
+        flush();
+        return pe * rs;
+    }
+};
+
 // ------------------------------------------------------------------ per-event state
-template <int P, bool DBG>
+// WONLY: only the event weight is wanted (the accept-reject mask pass): no kinematics, and the weight -- like the
+// maximum weight -- is accumulated as a product in wacc instead of being formed factor by factor.
+template <int P, bool DBG, bool WONLY = false>
 struct Ctx {
+    static constexpr bool wonly = WONLY && !PS_EXACT;
     double px[P], py[P], pz[P], en[P], ms[P];
+    WmaxAcc wacc;  // 1 / (product of the two-body momenta of the event), wonly
     unsigned long long seed, event;
     const double* dbg_row;
     unsigned int w[4];  // Philox block currently being consumed
@@ -140,29 +168,6 @@ __device__ __forceinline__ double pdk_x(double a, double b, double c) {
 }
 __device__ __forceinline__ double pdk(double a, double b, double c) { return sqrt(pdk_x(a, b, c)) / (2.0 * a); }
 
-// Fast variant: the maximum weight of a tree is a product of two-body momenta sqrt(x_i)/(2 a_i) over all decaying
-// nodes; only its reciprocal is needed to normalise the weight, so the factors are multiplied up first --
-// prod(2 a_i) * rsqrt(prod x_i) -- with one reciprocal square root per four factors (x_i ~ M^4: four of them stay
-// far from overflow for any mass scale) instead of a square root and a reciprocal per factor.
-struct WmaxAcc {
-    double rs = 1.0, px = 1.0, pe = 1.0;
-    int cnt = 0, n = 0;
-    __device__ __forceinline__ void add(double x, double two_a) {
-        px = cnt == 0 ? x : px * x;
-        pe = n == 0 ? two_a : pe * two_a;
-        ++n;
-        if (++cnt == 4) flush();
-    }
-    __device__ __forceinline__ void flush() {
-        if (cnt) rs = rs * rsqrt_pos(px);
-        cnt = 0;
-    }
-    __device__ __forceinline__ double inverse() {  // 1 / w_max
-        flush();
-        return pe * rs;
-    }
-};
-
 // phasespace.py:288-298
 template <int N>
 __device__ __forceinline__ double get_w_max(double avail, const double (&m)[N]) {
@@ -206,17 +211,41 @@ __device__ __forceinline__ void lorentz_boost_exact(double& x, double& y, double
     e = gamma * (e + bp);
 }
 
+__device__ __forceinline__ void cmp_exchange(double& a, double& b) {
+    const double lo = fmin(a, b), hi = fmax(a, b);
+    a = lo, b = hi;
+}
+// Sorting networks: optimal (fewest comparators) up to 8 elements -- 1, 3, 5, 9, 12, 16, 19 instead of the K(K-1)/2
+// of insertion order; a compare-exchange of doubles is five instructions on sm_100a (no fp64 min/max).
 template <int K>
 __device__ __forceinline__ void sort_network(double (&r)[K]) {
+#define PS_CE(i, j) cmp_exchange(r[i], r[j])
+    if constexpr (K == 2) {
+        PS_CE(0, 1);
+    } else if constexpr (K == 3) {
+        PS_CE(0, 2); PS_CE(0, 1); PS_CE(1, 2);
+    } else if constexpr (K == 4) {
+        PS_CE(0, 2); PS_CE(1, 3); PS_CE(0, 1); PS_CE(2, 3); PS_CE(1, 2);
+    } else if constexpr (K == 5) {
+        PS_CE(0, 3); PS_CE(1, 4); PS_CE(0, 2); PS_CE(1, 3); PS_CE(0, 1); PS_CE(2, 4); PS_CE(1, 2); PS_CE(3, 4); PS_CE(2, 3);
+    } else if constexpr (K == 6) {
+        PS_CE(0, 5); PS_CE(1, 3); PS_CE(2, 4); PS_CE(1, 2); PS_CE(3, 4); PS_CE(0, 3); PS_CE(2, 5); PS_CE(0, 1); PS_CE(2, 3);
+        PS_CE(4, 5); PS_CE(1, 2); PS_CE(3, 4);
+    } else if constexpr (K == 7) {
+        PS_CE(0, 6); PS_CE(2, 3); PS_CE(4, 5); PS_CE(0, 2); PS_CE(1, 4); PS_CE(3, 6); PS_CE(0, 1); PS_CE(2, 5); PS_CE(3, 4);
+        PS_CE(1, 2); PS_CE(4, 6); PS_CE(2, 3); PS_CE(4, 5); PS_CE(1, 2); PS_CE(3, 4); PS_CE(5, 6);
+    } else if constexpr (K == 8) {
+        PS_CE(0, 2); PS_CE(1, 3); PS_CE(4, 6); PS_CE(5, 7); PS_CE(0, 4); PS_CE(1, 5); PS_CE(2, 6); PS_CE(3, 7); PS_CE(0, 1);
+        PS_CE(2, 3); PS_CE(4, 5); PS_CE(6, 7); PS_CE(2, 4); PS_CE(3, 5); PS_CE(1, 4); PS_CE(3, 6); PS_CE(1, 2); PS_CE(3, 4);
+        PS_CE(5, 6);
+    } else {
 #pragma unroll
-    for (int i = 1; i < K; ++i) {
+        for (int i = 1; i < K; ++i) {
 #pragma unroll
-        for (int j = i; j > 0; --j) {
-            const double a = r[j - 1], b = r[j];
-            r[j - 1] = fmin(a, b);
-            r[j] = fmax(a, b);
+            for (int j = i; j > 0; --j) PS_CE(j - 1, j);
         }
     }
+#undef PS_CE
 }
 
 // ------------------------------------------------------------------ child masses (phasespace.py:335-354)
@@ -460,7 +489,17 @@ __device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long 
         }
     }
 #else
-    {
+    if constexpr (C::wonly) {
+#pragma unroll
+        for (int j = 0; j < N - 1; ++j) {
+            const double a = inv[j + 1], b = inv[j], cc = m[j + 1];
+            const double amb = a - b, apb = a + b;
+            c.wacc.add((amb - cc) * (apb + cc) * (amb + cc) * (apb - cc), a + a);
+        }
+        wn = 1.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) x[j] = y[j] = z[j] = e[j] = 0.0;
+    } else {
         double pd[N - 1], ra[N - 1], enew[N], esub[N - 1];
 #pragma unroll
         for (int j = 0; j < N - 1; ++j) {
@@ -776,7 +815,7 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
         const long long i = tile * PS_BLOCK + threadIdx.x;
         bool accept = false;
         if (i < n) {
-            Ctx<P, false> c;
+            Ctx<P, false, true> c;
             c.seed = prm.seed;
             c.event = prm.first_event + (unsigned long long)i;
             c.dbg_row = nullptr;
@@ -790,7 +829,9 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
 #if PS_EXACT
             accept = u * w_bound * w_max < w;
 #else
-            accept = u * w_bound < w * inv_w_max;
+            // w = 1 / c.wacc.inverse(): u w_bound < w / w_max  <=>  u w_bound / w < 1 / w_max  (w = 0: inf, rejected)
+            accept = u * w_bound * c.wacc.inverse() < inv_w_max;
+            (void)w;
 #endif
             bad_any |= c.bad;
         }
