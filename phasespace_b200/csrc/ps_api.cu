@@ -95,6 +95,7 @@ struct ps_tree {
     std::vector<double> min_mass;
     int top = -1, n_particles = 0, n_draws = 0, n_user = 0;
     bool has_grandchildren = false, resonant_leaf = false;
+    bool two_body_only = true;  // every decaying node has exactly two children (Pt::two_body_only)
     double w_max = NAN;
     std::string signature;
     PsParams base;  // constant part of the parameter block
@@ -281,6 +282,7 @@ extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tre
     t->n_draws = next_col;
     memset(&t->base, 0, sizeof(PsParams));
     t->base.mass[0] = nodes[t->top].mass;
+    if (t->children[t->top].size() != 2) t->two_body_only = false;
     for (int i = 0; i < n_nodes; ++i) {
         if (i == t->top) continue;
         const int s1 = t->slot[i] + 1;
@@ -298,6 +300,7 @@ extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tre
             t->base.user_col[s1] = t->user_col[i];
         }
         if (!t->children[i].empty()) t->has_grandchildren = true;
+        if (!t->children[i].empty() && t->children[i].size() != 2) t->two_body_only = false;
         if (t->children[i].empty() && nodes[i].kind != PS_MASS_FIXED) t->resonant_leaf = true;
     }
     // user columns follow slot order so that the Python layer can fill them in generation order
@@ -523,7 +526,7 @@ int pick_grid(const ps_tree* t, const void* fn, long long n_events, int* grid, i
     const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
     int k = 0;
     long long g;
-    if (t->n_particles <= PS_CHUNKED_MAX_P) {  // must match CHUNKED in genbod_body
+    if (t->n_particles <= PS_CHUNKED_MAX_P || t->two_body_only) {  // must match CHUNKED in genbod_body
         k = 16;
         while (k > 1 && tiles / k < (long long)sms * per_sm * 4) k >>= 1;  // keep several waves of CTAs
         while ((tiles + k - 1) / k > 2147483647LL) k <<= 1;

@@ -55,9 +55,10 @@ del pt, eta, phi, px, py, pz
 run("3: B0->4pi + per-event boost_to, n=1e8", ps.nbody_decay(B0, [PI] * 4), n8, boost=boost)
 del boost
 torch.cuda.empty_cache()
-for kind, fac in (("relbw", mf.relativistic_breitwigner_factory), ("gauss", mf.gauss_factory), ("bw", mf.breitwigner_factory)):
+for kind, fac in (("relbw", mf.relativistic_breitwigner_factory), ("gauss", mf.gauss_factory), ("bw", mf.breitwigner_factory),
+                  ("fixed-mass", None)):
     chain = ps.GenParticle("B0", B0).set_children(
-        ps.GenParticle("K*0", fac(895.81, 47.4)).set_children(ps.GenParticle("K+", K), ps.GenParticle("pi-", PI)),
+        ps.GenParticle("K*0", 895.81 if fac is None else fac(895.81, 47.4)).set_children(ps.GenParticle("K+", K), ps.GenParticle("pi-", PI)),
         ps.GenParticle("gamma", 0.0))
     run(f"4: B0->K*0(->K pi) gamma, {kind} K*0, n=1e8", chain, n8)
 ten = ps.nbody_decay(B0, [PI] * 10)
