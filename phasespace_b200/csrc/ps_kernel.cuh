@@ -335,7 +335,7 @@ __device__ __forceinline__ void genbod_step_fast(C& c, const double* pd, const d
     const double ua = c.template next<AB>();
     const double ub = c.template next<AB + 1>();
     const double cz = 2.0 * ua - 1.0;
-    const double sz = sqrt_pos(fma(-cz, cz, 1.0));
+    const double sz = sqrt_pos1(fma(-cz, cz, 1.0));
     double sy, cy;
     sincos_2pi(ub, sy, cy);
     const double t = sz * pd[K - 1];
@@ -508,9 +508,9 @@ __device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long 
             const double a = inv[j + 1], b = inv[j], cc = m[j + 1];
             const double amb = a - b, apb = a + b;
             const double xx = (amb - cc) * (apb + cc) * (amb + cc) * (apb - cc);
-            ra[j] = rcp_pos(a);
+            ra[j] = rcp_pos1(a);
             const double hra = 0.5 * ra[j];
-            pd[j] = sqrt_pos(xx) * hra;
+            pd[j] = sqrt_pos1(xx) * hra;
             enew[j + 1] = fma(amb, apb, cc * cc) * hra;  // (a^2 + c^2 - b^2) / 2a
             esub[j] = a - enew[j + 1];
         }
@@ -520,9 +520,9 @@ __device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long 
         genbod_steps_fast<N, AB0>(c, pd, ra, enew, esub, x, y, z, e, MakeSeq<N - 1>{});
         if constexpr (!REST) {
             // boost by the parent: u = gamma*beta = p/M, gamma = E/M;  p' = p + (u.p/(gamma+1) + E) u ; E' = gamma E + u.p
-            const double rM = rcp_pos(M);
+            const double rM = rcp_pos1(M);
             const double ux = ppx * rM, uy = ppy * rM, uz = ppz * rM, g = pe * rM;
-            const double g1 = rcp_pos(g + 1.0);
+            const double g1 = rcp_pos1(g + 1.0);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const double up = fma(ux, x[j], fma(uy, y[j], uz * z[j]));

@@ -115,15 +115,16 @@ __device__ __forceinline__ void relbw_limits(const SamplerConst& k, double lo, d
 }
 
 // generic solver: Newton in t with library functions, to full convergence
-static __device__ __noinline__ double relbw_solve_generic(const SamplerConst& k, double t_lo, double t_hi, double t, double target) {
-    const double ik2 = k.c4;
+// (scalars by value: a struct reference would make every caller spill the constants to its stack frame)
+static __device__ __noinline__ double relbw_solve_generic(double kappa, double inv_kappa, double ik2, double t_lo, double t_hi,
+                                                          double t, double target) {
     bool last = false;
 #pragma unroll 1
     for (int it = 0; it < 4 * PS_RELBW_MAX_ITERS; ++it) {
         const double z = tan(t);
-        const double y = z + k.c2;
+        const double y = z + kappa;
         const double b = fma(y, y, 1.0);
-        const double g = t + atan(y) + k.c3 * log(b / fma(z, z, 1.0)) - target;
+        const double g = t + atan(y) + inv_kappa * log(b / fma(z, z, 1.0)) - target;
         const double step = g * b * ik2;
         t = fmin(fmax(t - step, t_lo), t_hi);
         if (last) break;
@@ -203,9 +204,9 @@ __device__ __forceinline__ double sample_relbw(const SamplerConst& k, const doub
             z = zn;
             inv_zz1 = 1.0 / fma(z, z, 1.0);
         }
-        if (!done) z = relbw_solve_generic(k, t_lo, t_hi, t0, target);
+        if (!done) z = relbw_solve_generic(k.c2, k.c3, k.c4, t_lo, t_hi, t0, target);
     } else {
-        z = relbw_solve_generic(k, t_lo, t_hi, t0, target);
+        z = relbw_solve_generic(k.c2, k.c3, k.c4, t_lo, t_hi, t0, target);
     }
     return clamp_mass(fma(k.c1, z, k.c0), lo, hi);
 }
