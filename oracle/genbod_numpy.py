@@ -3,14 +3,20 @@
 TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import this module.  The product path (phasespace_b200) never does.
 
-PARITY STATUS: the reference itself (/root/reference/src/phasespace) cannot be imported here -- it
-needs TensorFlow >= 2.19 + tensorflow_probability, neither installed nor installable offline -- and
-its tests hold no numeric golden vectors for this path.  This file restates
-the reference op by op (``tnp`` is numpy-API compatible, so the restatement is mechanical: same
-operations, same association order, fp64, no FMA) and is PINNED by
+PARITY STATUS: PINNED against the reference's own source code.  The reference (/root/reference/src/phasespace)
+needs TensorFlow >= 2.19 + tensorflow_probability, neither installed nor installable offline; but the only TensorFlow
+surface its generator uses is ``tensorflow.experimental.numpy`` (a NumPy-compatible API), ``tf.function`` and
+``tf.random.Generator.uniform``.  tests/golden/make_reference_golden.py installs a stand-in ``tensorflow`` module that
+maps those to NumPy and to a table-driven generator, imports the reference UNMODIFIED and runs its
+``GenParticle.generate`` on fixed uniform tables for twelve trees (flat 2/3/4/5/10 bodies, per-event and one-row
+``boost_to``, K* gamma and K1 gamma chains with fixed and callable resonance masses, two decaying branches side by
+side); the outputs are committed as tests/golden/reference_vectors.npz.  This oracle, fed the same tables, reproduces
+every weight, maximum weight and 4-vector of those runs BIT FOR BIT (tests/test_oracle.py::
+test_oracle_matches_reference_source holds it to 1e-13 so that a different NumPy build may differ in the last bit of
+sin/cos).  It is also pinned by
   * the six events printed in the reference's README (README.rst:156-183), which are real outputs of
-    ``generate()`` for B0 -> K*(-> K+ pi-) gamma: tests/test_oracle.py recovers the four draws of each
-    event from the printed K* and K+ vectors, feeds them to this oracle and gets all four printed
+    ``generate()`` under TensorFlow for B0 -> K*(-> K+ pi-) gamma: tests/test_oracle.py recovers the four draws of
+    each event from the printed K* and K+ vectors, feeds them to this oracle and gets all four printed
     4-vectors back to the printed precision (tests/golden/readme_kstargamma.json),
   * the closed-form two-body energies of the same README block (E(K*)=2715.78804872, E(gamma)=2563.79195128),
   * the invariants the reference's own tests assert (shapes, w/w_max < 1, key order, error types),

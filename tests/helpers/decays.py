@@ -37,19 +37,25 @@ def k1_gamma_desc(k1_kind="gauss", kst_kind="gauss"):
 
 def to_oracle(desc):
     name, mass, kind, width, children = desc
-    k = orc.FIXED if kind == "fixed" else orc.KIND_NAMES[kind]
+    k = orc.FIXED if kind == "fixed" else (orc.USER if kind == "user" else orc.KIND_NAMES[kind])
     return orc.Part(name, mass, k, width, [to_oracle(c) for c in children])
 
 
-def to_gen(desc):
+def to_gen(desc, user_masses=None):
+    """``user`` nodes become GenParticles with a Python mass callable that returns ``user_masses[name]``."""
     from phasespace_b200 import GenParticle
     from phasespace_b200.fromdecay import mass_functions as mf
 
     name, mass, kind, width, children = desc
     if kind == "fixed":
         part = GenParticle(name, mass)
+    elif kind == "user":
+        import torch
+
+        table = torch.as_tensor(user_masses[name], dtype=torch.float64)
+        part = GenParticle(name, lambda min_mass, max_mass, n_events, table=table: table.to(min_mass.device))
     else:
         part = GenParticle(name, mf.DEFAULT_CONVERTER[kind](mass, width))
     if children:
-        part.set_children(*[to_gen(c) for c in children])
+        part.set_children(*[to_gen(c, user_masses) for c in children])
     return part

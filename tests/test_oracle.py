@@ -238,3 +238,24 @@ def test_fonll_oracle_is_numpy_choice():
     draws = np.stack([rs.random_sample(n), rs.random_sample(n), rs.random_sample(n)], axis=1)
     got = orc.generate_fonll(mass, pt_centers, pt_values, eta_centers, eta_values, draws)
     np.testing.assert_array_equal(got, ref.transpose())
+
+
+@pytest.mark.parametrize("case", list(__import__("tests.helpers.reference_cases", fromlist=["CASES"]).CASES))
+def test_oracle_matches_reference_source(case):
+    """The oracle against the reference's OWN source code run on NumPy (tests/golden/make_reference_golden.py): same
+    uniform draws in the reference's draw order, same boosts, same callable masses.  The two differ at most in the
+    association of a few sums (numpy's pairwise reduction inside the reference run), hence 1e-13 and not bit equality."""
+    from tests.helpers import reference_cases as R
+
+    ref = R.load(case)
+    tree = D.to_oracle(R.CASES[case])
+    n = ref["draws"].shape[0]
+    assert orc.n_draws(tree) == ref["draws"].shape[1]
+    w, w_max, parts = orc.generate(tree, n, ref["draws"], boost_to=ref["boost"], normalize_weights=False,
+                                   user_masses=ref["user_masses"] or None)
+    assert list(parts) == ref["names"]  # the reference's dict order (phasespace.py:547-570)
+    np.testing.assert_allclose(w, ref["weights"], rtol=1e-13)
+    np.testing.assert_allclose(w_max, ref["weights_max"], rtol=1e-13)
+    scale = D.B0_MASS if ref["boost"] is None else float(np.max(ref["boost"][:, 3]))
+    for k, name in enumerate(ref["names"]):
+        assert np.max(np.abs(parts[name] - ref["particles"][k])) <= 1e-13 * scale, name
