@@ -287,3 +287,26 @@ def test_fonll_boost_generator():
     assert float((total - got).abs().max()) / scale < 1e-12
     with pytest.raises(ValueError):
         generate_fonll(B0_MASS, (pt_edges, pt_values[:-1]), (eta_centers, eta_values), 10)
+
+
+@pytest.mark.parametrize("n", [1, 31, 255, 257, 100_003])
+def test_no_writes_outside_the_output_buffers(n):
+    """Canaries around every output buffer (compute-sanitizer is not available on the GPU pool): odd sizes, 3-body,
+    chunked 2-body grid and a chain; nothing outside [0, n) may be touched and everything inside must be written."""
+    pad, sentinel = 64, -12345.678
+    dev = torch.device("cuda")
+    for decay in (phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3), phasespace.nbody_decay(B0_MASS, [PION_MASS, D.KAON_MASS]),
+                  D.to_gen(D.kstar_gamma_desc("relbw"))):
+        comp = decay.compile()
+        P = comp.n_particles
+        wbuf = torch.full((n + 2 * pad,), sentinel, dtype=torch.float64, device=dev)
+        mbuf = torch.full((n + 2 * pad,), sentinel, dtype=torch.float64, device=dev)
+        pbuf = torch.full((P, n + 2 * pad, 4), sentinel, dtype=torch.float64, device=dev)
+        out = {"weights": wbuf[pad:pad + n], "weights_max": mbuf[pad:pad + n], "particles": pbuf[:, pad:pad + n, :]}
+        comp.launch(n, seed=3, normalize_weights=False, out=out)
+        torch.cuda.synchronize()
+        for buf in (wbuf, mbuf):
+            assert bool((buf[:pad] == sentinel).all()) and bool((buf[pad + n:] == sentinel).all())
+            assert not bool((buf[pad:pad + n] == sentinel).any())
+        assert bool((pbuf[:, :pad] == sentinel).all()) and bool((pbuf[:, pad + n:] == sentinel).all())
+        assert not bool((pbuf[:, pad:pad + n] == sentinel).any())
