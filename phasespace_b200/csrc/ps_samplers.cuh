@@ -88,6 +88,13 @@ __device__ __forceinline__ double sample_cauchy(const SamplerConst& k, const dou
 #define PS_RELBW_ALPHA_OK 0.01
 #define PS_RELBW_ALPHA_RETRY 0.2
 
+// fp32 special-function unit, flush-to-zero forms: the default (non-ftz) forms of the CUDA fast intrinsics wrap every
+// MUFU in denormal scaling code, three to six extra instructions each
+__device__ __forceinline__ float f32_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f32_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f32_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f32_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // slowly varying part of G:  atan(z+kappa) + ln(((z+kappa)^2+1) inv_zz1)/kappa,   inv_zz1 = 1/(z^2+1)
 template <bool FAR>
 __device__ __forceinline__ double relbw_slow(const SamplerConst& k, double z, double inv_zz1) {
@@ -153,22 +160,21 @@ __device__ __forceinline__ double sample_relbw(const SamplerConst& k, const doub
         float tf = (float)t0;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-            float s, c;
-            __sincosf(tf, &s, &c);
-            c = fmaxf(c, 1e-6f);
+            const float s = f32_sin(tf);
+            const float c = fmaxf(f32_cos(tf), 1e-6f);
             const float c2 = c * c;
-            const float zf = __fdividef(s, c);
+            const float zf = s * f32_rcp(c);
             const float y = zf + kf;
-            const float iy = __fdividef(1.0f, y);
+            const float iy = f32_rcp(y);
             const float iy2 = iy * iy;
             const float at = 1.5707964f - iy * (1.0f - iy2 * (0.33333334f - 0.2f * iy2));
             const float b = fmaf(y, y, 1.0f);
             const float bc = b * c2;
-            const float g = (tf - tgf) + fmaf(__logf(bc), ikf, at);
-            const float n = g * b * ik2f;                 // Newton step
-            const float r = -y * __fdividef(1.0f, bc);    // G''/(2 G') in t
+            const float g = (tf - tgf) + fmaf(f32_lg2(bc), ikf * 0.6931472f, at);
+            const float n = g * b * ik2f;        // Newton step
+            const float r = -y * f32_rcp(bc);    // G''/(2 G') in t
             const float den = fmaf(-n, r, 1.0f);
-            const float step = den > 0.5f ? __fdividef(n, den) : n;
+            const float step = den > 0.5f ? n * f32_rcp(den) : n;
             tf = fminf(fmaxf(tf - step, tlof), thif);
         }
         // 2./3. fp64: evaluate G once, fourth-order inverse series in z
