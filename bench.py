@@ -126,7 +126,8 @@ def _cpu_baseline(min_seconds=10.0):
     bench.close()
     out = {
         "value": events / seconds, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"numpy restatement of the reference (oracle/genbod_numpy.py), {passes} passes x {cores} worker "
+        "sample": f"numpy restatement of the reference (oracle/genbod_numpy.py; bit-identical to the reference's own "
+                  f"source run on NumPy, tests/golden/make_reference_golden.py), {passes} passes x {cores} worker "
                   f"processes x {per_worker} events = {events} events in {seconds:.1f} s; the reference's own "
                   "TensorFlow CPU path cannot be installed here",
     }
@@ -157,7 +158,8 @@ def run_reference(args, rank, world):
     bench.close()
     value = total / t_total
     sample = (f"each step = {cores} worker processes x {per_worker} events of the numpy restatement "
-              "(oracle/genbod_numpy.py); reference TensorFlow path not installable here")
+              "(oracle/genbod_numpy.py; bit-identical to the reference's own source run on NumPy); reference TensorFlow "
+              "path not installable here")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
