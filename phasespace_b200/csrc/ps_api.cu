@@ -8,6 +8,8 @@
 // CUDA device every compute entry point fails with PS_E_CUDA.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <cmath>
@@ -405,6 +407,7 @@ struct Nvrtc {
     nvrtcResult_t (*GetCUBIN)(nvrtcProgram_t, char*) = nullptr;
     nvrtcResult_t (*DestroyProgram)(nvrtcProgram_t*) = nullptr;
     const char* (*GetErrorString)(nvrtcResult_t) = nullptr;
+    nvrtcResult_t (*Version)(int*, int*) = nullptr;
 };
 
 Nvrtc* load_nvrtc() {
@@ -431,12 +434,75 @@ Nvrtc* load_nvrtc() {
     PS_SYM(GetCUBIN, "nvrtcGetCUBIN");
     PS_SYM(DestroyProgram, "nvrtcDestroyProgram");
     PS_SYM(GetErrorString, "nvrtcGetErrorString");
+    PS_SYM(Version, "nvrtcVersion");
 #undef PS_SYM
     if (!n.CreateProgram || !n.CompileProgram || !n.GetCUBIN) {
         n.handle = nullptr;
         return nullptr;
     }
     return &n;
+}
+
+// On-disk cache of NVRTC results: $PS_B200_CACHE_DIR, else $XDG_CACHE_HOME/phasespace_b200, else
+// ~/.cache/phasespace_b200; PS_B200_CACHE_DIR="" (empty) disables it.  The file name hashes everything the cubin
+// depends on: the generated source, the embedded headers, the compile options and the NVRTC version.
+uint64_t fnv1a(const void* data, size_t n, uint64_t h) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+}
+
+std::string jit_cache_dir() {
+    const char* env = getenv("PS_B200_CACHE_DIR");
+    std::string dir;
+    if (env) {
+        if (!*env) return "";
+        dir = env;
+    } else if (const char* xdg = getenv("XDG_CACHE_HOME"); xdg && *xdg) {
+        dir = std::string(xdg) + "/phasespace_b200";
+    } else if (const char* home = getenv("HOME"); home && *home) {
+        dir = std::string(home) + "/.cache";
+        mkdir(dir.c_str(), 0755);
+        dir += "/phasespace_b200";
+    } else {
+        return "";
+    }
+    mkdir(dir.c_str(), 0755);
+    struct stat st;
+    return (stat(dir.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) ? dir : "";
+}
+
+bool read_file(const std::string& path, std::vector<char>& out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    bool ok = n > 0;
+    if (ok) {
+        out.resize((size_t)n);
+        ok = fread(out.data(), 1, (size_t)n, f) == (size_t)n;
+    }
+    fclose(f);
+    return ok;
+}
+
+void write_file_atomic(const std::string& path, const std::vector<char>& data) {
+    const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+    fclose(f);
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) unlink(tmp.c_str());
+}
+
+int load_cubin(const std::vector<char>& cubin, const void** fn_out) {
+    cudaLibrary_t lib;
+    PS_CUDA(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    cudaKernel_t kern;
+    PS_CUDA(cudaLibraryGetKernel(&kern, lib, "ps_jit_kernel"));
+    *fn_out = (const void*)kern;
+    return 0;
 }
 
 // Specialise ps_kernel.cuh for one tree: returns a cudaKernel_t (usable with cudaLaunchKernel).
@@ -459,6 +525,21 @@ int jit_compile(const KernelKey& key, const void** fn_out) {
         hdr_text.push_back(h->text);
         hdr_name.push_back(h->name);
     }
+    std::string cache_path;
+    if (const std::string dir = jit_cache_dir(); !dir.empty()) {
+        uint64_t h = fnv1a(src.data(), src.size(), 1469598103934665603ull);
+        for (const char* t : hdr_text) h = fnv1a(t, strlen(t), h);
+        int major = 0, minor = 0;
+        if (rt->Version) rt->Version(&major, &minor);
+        const std::string extra = "sm_100a;c++17;exact=" + std::to_string(key.exact) + ";nvrtc=" + std::to_string(major) + "." + std::to_string(minor);
+        h = fnv1a(extra.data(), extra.size(), h);
+        char name[64];
+        snprintf(name, sizeof(name), "/ps_%016llx.cubin", (unsigned long long)h);
+        cache_path = dir + name;
+        std::vector<char> cached;
+        if (read_file(cache_path, cached) && load_cubin(cached, fn_out) == 0) return 0;
+        (void)cudaGetLastError();  // a stale or truncated file: compile again and overwrite it
+    }
     nvrtcProgram_t prog = nullptr;
     nvrtcResult_t rc = rt->CreateProgram(&prog, src.c_str(), "ps_jit.cu", (int)hdr_text.size(), hdr_text.data(), hdr_name.data());
     if (rc != 0) return fail(PS_E_COMPILE, "nvrtcCreateProgram failed: %s", rt->GetErrorString ? rt->GetErrorString(rc) : "?");
@@ -480,12 +561,9 @@ int jit_compile(const KernelKey& key, const void** fn_out) {
     std::vector<char> cubin(n);
     rt->GetCUBIN(prog, cubin.data());
     rt->DestroyProgram(&prog);
-    cudaLibrary_t lib;
-    PS_CUDA(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-    cudaKernel_t kern;
-    PS_CUDA(cudaLibraryGetKernel(&kern, lib, "ps_jit_kernel"));
-    *fn_out = (const void*)kern;
-    return 0;
+    const int rc_load = load_cubin(cubin, fn_out);
+    if (rc_load == 0 && !cache_path.empty()) write_file_atomic(cache_path, cubin);
+    return rc_load;
 }
 
 int get_kernel(const ps_tree* t, int variant, int boost, int dbg, int exact, const void** fn) {

@@ -310,3 +310,38 @@ def test_no_writes_outside_the_output_buffers(n):
             assert not bool((buf[pad:pad + n] == sentinel).any())
         assert bool((pbuf[:, :pad] == sentinel).all()) and bool((pbuf[:, pad + n:] == sentinel).all())
         assert not bool((pbuf[:, pad:pad + n] == sentinel).any())
+
+
+def test_jit_disk_cache(tmp_path):
+    """NVRTC results are cached on disk (PS_B200_CACHE_DIR): a second process loads the cubin instead of compiling,
+    with identical events; an empty PS_B200_CACHE_DIR disables the cache."""
+    import subprocess
+    import sys
+    import time
+
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    script = ("import sys, time; sys.path.insert(0, %r)\n"
+              "import torch, phasespace_b200 as ps\n"
+              "ps.nbody_decay(5279.58, [139.57018] * 3).generate(10); torch.cuda.synchronize()\n"  # CUDA context, library
+              "d = ps.nbody_decay(5279.58, [139.57018] * 12)\n"  # 12 bodies: never compiled ahead of time
+              "t0 = time.perf_counter(); w, p = d.generate(1000, seed=4); torch.cuda.synchronize()\n"
+              "print(time.perf_counter() - t0, float(w.sum()), float(p['p_11'].sum()))\n") % root
+
+    def run(cache_dir):
+        env = dict(os.environ, PS_B200_CACHE_DIR=cache_dir)
+        out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        t, sw, sp = out.stdout.split()[-3:]
+        return float(t), sw, sp
+
+    cache = str(tmp_path / "jit")
+    os.makedirs(cache)
+    t_cold, sw0, sp0 = run(cache)
+    files = [f for f in os.listdir(cache) if f.endswith(".cubin")]
+    assert len(files) == 1, files
+    t_warm, sw1, sp1 = run(cache)
+    assert (sw0, sp0) == (sw1, sp1)
+    assert t_warm < t_cold, (t_cold, t_warm)
+    assert [f for f in os.listdir(cache) if f.endswith(".cubin")] == files
+    _, sw2, sp2 = run("")  # disabled
+    assert (sw2, sp2) == (sw0, sp0) and sorted(os.listdir(cache)) == sorted(files)
