@@ -20,7 +20,7 @@ from .random import SeedLike, get_rng
 
 def generate_histograms(decay, n_events: int, seed: SeedLike = None, *, bins: int = 100, p_range=(-3000.0, 3000.0),
                         e_range=(0.0, 3000.0), boost_to=None, normalize: bool = True, chunk_events: int = 1 << 30,
-                        exact: bool = False, w_cap: float | None = None):
+                        exact: bool = False, w_cap: float | None = None, first_event: int | None = None):
     """Weighted histograms of ``decay.generate(n_events, seed=seed)`` without materialising the events.
 
     Returns ``(particle_histos, weight_histo)``: ``particle_histos[name]`` is a ``(4, bins)`` CUDA tensor (rows px, py,
@@ -31,6 +31,8 @@ def generate_histograms(decay, n_events: int, seed: SeedLike = None, *, bins: in
     ``w_cap`` is the expected upper bound of the normalised weights: weights within 26 binary orders of magnitude
     below it are accumulated in exact fixed point with native shared-memory atomics, the others (still correctly)
     with slower fp64 atomics.  By default it is four times the largest weight of a 32768-event pilot sample.
+    ``first_event`` (with an integer ``seed``) histograms the events ``[first_event, first_event + n_events)`` of the
+    stream instead of the generator's next ones: the multi-GPU entry (``sharding.generate_histograms_sharded``).
     """
     device = _device()
     n = int(n_events)
@@ -39,7 +41,7 @@ def generate_histograms(decay, n_events: int, seed: SeedLike = None, *, bins: in
         raise ValueError("fused histograms need in-kernel mass functions (no arbitrary Python callables)")
     decay._mark_generate_called()
     rng = get_rng(seed)
-    first = rng.reserve(n)
+    first = rng.reserve(n) if first_event is None else int(first_event)
     P = compiled.n_particles
     hist = torch.zeros((4 * P + 1, bins), dtype=torch.float64, device=device)
     err = torch.zeros((1,), dtype=torch.int32, device=device)

@@ -76,3 +76,31 @@ def allreduce_count(count: int, device=None, group=None) -> int:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return int(t.item())
+
+
+def allreduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
+    """SUM all-reduce of a small tensor (histograms, counters); identity in a single process."""
+    out = t.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def generate_histograms_sharded(decay, n_events: int, seed: int, *, group=None, normalize: bool = True, **kwargs):
+    """``histogram.generate_histograms`` over all ranks: every rank bins its own contiguous range of event indices on
+    its GPU and the per-rank histograms (a few kB) are summed with one all-reduce.  Returns the global histograms on
+    every rank, in the same form as ``generate_histograms``."""
+    from .histogram import generate_histograms
+
+    rank, world = _rank_world(group)
+    first, count = shard_range(n_events, rank, world)
+    parts, weight_hist = generate_histograms(decay, count, seed=int(seed), normalize=False, first_event=first, **kwargs)
+    names = list(parts)
+    flat = torch.cat([parts[name].reshape(-1) for name in names] + [weight_hist.reshape(-1)])
+    flat = allreduce_sum(flat, group=group)
+    bins = weight_hist.numel()
+    rows = flat.view(-1, bins)
+    if normalize:
+        sums = rows.sum(dim=1, keepdim=True)
+        rows = rows / torch.where(sums > 0, sums, torch.ones_like(sums))
+    return {name: rows[4 * k:4 * k + 4] for k, name in enumerate(names)}, rows[4 * len(names)]

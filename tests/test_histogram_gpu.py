@@ -58,3 +58,21 @@ def test_fused_histograms_with_boost():
     np.testing.assert_allclose(got_w.cpu().numpy(), ref_w, rtol=1e-12)
     with pytest.raises(ValueError):
         generate_histograms(decay, n, seed=seed, bins=5000)
+
+
+def test_sharded_histograms_single_process_and_ranges():
+    """generate_histograms_sharded in one process is generate_histograms; histogramming two index ranges separately
+    (what two ranks do) and adding them gives the histograms of the whole range."""
+    from phasespace_b200 import sharding
+
+    decay = phasespace.nbody_decay(D.B0_MASS, [D.PION_MASS] * 3)
+    n, seed = 200_000, 5
+    parts, w = generate_histograms(decay, n, seed=seed, normalize=False, first_event=0)
+    sh_parts, sh_w = sharding.generate_histograms_sharded(decay, n, seed, normalize=False)
+    assert torch.equal(w, sh_w) and all(torch.allclose(parts[k], sh_parts[k], rtol=1e-12) for k in parts)
+    (f0, c0), (f1, c1) = sharding.shard_range(n, 0, 2), sharding.shard_range(n, 1, 2)
+    pa, wa = generate_histograms(decay, c0, seed=seed, normalize=False, first_event=f0)
+    pb, wb = generate_histograms(decay, c1, seed=seed, normalize=False, first_event=f1)
+    assert torch.equal(wa + wb, w)
+    for k in parts:
+        np.testing.assert_allclose((pa[k] + pb[k]).cpu().numpy(), parts[k].cpu().numpy(), rtol=1e-11)

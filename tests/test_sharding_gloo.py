@@ -35,7 +35,8 @@ def _worker(rank, world, port, n_events, out):
         stats = torch.stack([w.max(), w.sum(), (w * w).sum(), torch.tensor(10.0 + rank, dtype=torch.float64)])
         red = sharding.allreduce_stats(stats)
         total = sharding.allreduce_count(count)
-        out[rank] = (first, count, red.tolist(), total)
+        hist = sharding.allreduce_sum(torch.bincount((w * 10).long(), minlength=10).to(torch.float64))
+        out[rank] = (first, count, red.tolist(), total, hist.tolist())
     finally:
         dist.destroy_process_group()
 
@@ -52,6 +53,7 @@ def test_two_rank_statistics_allreduce():
     assert out[0][0] == 0 and out[1][0] == out[0][1] and out[0][1] + out[1][1] == n_events
     for rank in range(world):
         assert out[rank][3] == n_events
+        assert out[rank][4] == torch.bincount((w * 10).long(), minlength=10).to(torch.float64).tolist()
         for got, want in zip(out[rank][2], expect):
             assert got == pytest.approx(want, rel=1e-12)
 
