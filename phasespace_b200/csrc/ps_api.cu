@@ -804,30 +804,93 @@ extern "C" int ps_generate_host(const ps_tree* tree, uint64_t seed, uint64_t fir
 // ---------------------------------------------------------------------------------- unweighting
 namespace {
 
-// exclusive scan of int32 tile counts into int64 offsets; one CTA, each thread scans a segment
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(const int* counts, long long n, long long* offsets, long long* total) {
-    __shared__ long long seg[1024];
-    const int t = threadIdx.x;
-    const long long per = (n + 1023) / 1024;
-    const long long lo = per * t < n ? per * t : n, hi = per * (t + 1) < n ? per * (t + 1) : n;
-    long long s = 0;
-    for (long long i = lo; i < hi; ++i) s += counts[i];
-    seg[t] = s;
+// Exclusive scan of int32 tile counts into int64 offsets, three small kernels over segments of PS_SCAN_SEG tiles:
+//   1. every CTA sums its segment (coalesced loads) and parks the sum in offsets[first tile of the segment];
+//   2. one CTA scans those parked sums in place (exclusive) and writes the grand total;
+//   3. every CTA reads its segment's offset, scans its counts in shared memory and writes the final offsets
+//      (the first tile of a segment gets exactly the value parked there, so no scratch buffer is needed).
+#define PS_SCAN_SEG 2048
+#define PS_SCAN_THREADS 256
+
+__device__ __forceinline__ long long block_exclusive_scan(long long v, long long* warp_sums, long long* block_total) {
+    // exclusive scan of one value per thread over a CTA of PS_SCAN_THREADS threads (or 1024 in phase 2)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
     __syncthreads();
-    if (t == 0) {
-        long long run = 0;
-        for (int k = 0; k < 1024; ++k) {
-            const long long v = seg[k];
-            seg[k] = run;
-            run += v;
+    if (wid == 0) {
+        long long w = lane < n_warps ? warp_sums[lane] : 0;
+        long long wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long up = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += up;
         }
-        if (total) *total = run;
+        if (lane < n_warps) warp_sums[lane] = wi - w;  // exclusive prefix of the warp totals
+        if (lane == 31) *block_total = wi;
     }
     __syncthreads();
-    long long run = seg[t];
-    for (long long i = lo; i < hi; ++i) {
-        offsets[i] = run;
-        run += counts[i];
+    const long long out = warp_sums[wid] + incl - v;
+    __syncthreads();  // warp_sums / block_total may be reused by the caller's next round
+    return out;
+}
+
+__global__ void __launch_bounds__(PS_SCAN_THREADS) scan_phase1_kernel(const int* counts, long long n, long long* offsets) {
+    __shared__ long long warp_sums[32];
+    __shared__ long long total;
+    const long long base = (long long)blockIdx.x * PS_SCAN_SEG;
+    long long s = 0;
+#pragma unroll
+    for (int k = 0; k < PS_SCAN_SEG / PS_SCAN_THREADS; ++k) {
+        const long long i = base + k * PS_SCAN_THREADS + threadIdx.x;
+        if (i < n) s += counts[i];
+    }
+    (void)block_exclusive_scan(s, warp_sums, &total);
+    if (threadIdx.x == 0) offsets[base] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_phase2_kernel(long long* offsets, long long n_segments, long long* total_out) {
+    __shared__ long long warp_sums[32];
+    __shared__ long long total;
+    long long carry = 0;
+    for (long long first = 0; first < n_segments; first += blockDim.x) {
+        const long long seg = first + threadIdx.x;
+        const long long v = seg < n_segments ? offsets[seg * PS_SCAN_SEG] : 0;
+        const long long excl = block_exclusive_scan(v, warp_sums, &total);
+        if (seg < n_segments) offsets[seg * PS_SCAN_SEG] = carry + excl;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(PS_SCAN_THREADS) scan_phase3_kernel(const int* counts, long long n, long long* offsets) {
+    __shared__ int seg_counts[PS_SCAN_SEG];
+    __shared__ long long warp_sums[32];
+    __shared__ long long total;
+    constexpr int PER = PS_SCAN_SEG / PS_SCAN_THREADS;
+    const long long base = (long long)blockIdx.x * PS_SCAN_SEG;
+    const long long seg_offset = offsets[base];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const long long i = base + k * PS_SCAN_THREADS + threadIdx.x;
+        seg_counts[k * PS_SCAN_THREADS + threadIdx.x] = i < n ? counts[i] : 0;
+    }
+    __syncthreads();  // also orders the read of offsets[base] before thread 0 overwrites it below
+    long long mine = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) mine += seg_counts[threadIdx.x * PER + k];
+    long long run = seg_offset + block_exclusive_scan(mine, warp_sums, &total);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const long long i = base + threadIdx.x * PER + k;
+        if (i < n) offsets[i] = run;
+        run += seg_counts[threadIdx.x * PER + k];
     }
 }
 
@@ -880,9 +943,13 @@ extern "C" int ps_unweight_mask(const ps_tree* tree, uint64_t seed, uint64_t fir
 
 extern "C" int ps_unweight_scan(const int32_t* tile_counts, int64_t n_tiles, int64_t* tile_offsets, int64_t* total, void* stream) {
     if (!tile_counts || !tile_offsets || n_tiles < 0) return fail(PS_E_INVALID, "null argument");
-    scan_tiles_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tile_counts, n_tiles, (long long*)tile_offsets, (long long*)total);
+    const long long n_segments = (n_tiles + PS_SCAN_SEG - 1) / PS_SCAN_SEG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_segments > 0) scan_phase1_kernel<<<(unsigned)n_segments, PS_SCAN_THREADS, 0, st>>>(tile_counts, n_tiles, (long long*)tile_offsets);
+    scan_phase2_kernel<<<1, 1024, 0, st>>>((long long*)tile_offsets, n_segments, (long long*)total);
+    if (n_segments > 0) scan_phase3_kernel<<<(unsigned)n_segments, PS_SCAN_THREADS, 0, st>>>(tile_counts, n_tiles, (long long*)tile_offsets);
     PS_CUDA(cudaGetLastError());
-    g_launches.fetch_add(1);
+    g_launches.fetch_add(n_segments > 0 ? 3 : 1);
     return 0;
 }
 
