@@ -768,7 +768,9 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
 #if PS_EXACT
         st_wmax = warp_max(st_wmax);
 #else
-        double st_wmax = warp_max(1.0 / st_inv_min);  // no events: 1/inf = 0
+        // no events: 1/inf = 0; an event-independent w_max is reported exactly, not as 1 / (1 / w_max)
+        constexpr bool WMAX_CONST = !(BOOST || Tree::resonant_leaf_below);
+        double st_wmax = warp_max(WMAX_CONST ? (st_inv_min == prm.inv_wmax_const ? prm.wmax_const : 0.0) : 1.0 / st_inv_min);
 #endif
         if (lane == 0) {
             red[0][wid] = st_max;

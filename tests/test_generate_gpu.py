@@ -345,3 +345,27 @@ def test_jit_disk_cache(tmp_path):
     assert [f for f in os.listdir(cache) if f.endswith(".cubin")] == files
     _, sw2, sp2 = run("")  # disabled
     assert (sw2, sp2) == (sw0, sp0) and sorted(os.listdir(cache)) == sorted(files)
+
+
+@pytest.mark.parametrize("n", [1, 1000, 300_001])
+def test_kernel_epilogue_statistics(n):
+    """The generator's own epilogue [max w, sum w, sum w^2, max w_max] (what the multi-GPU all-reduce combines)."""
+    dev = torch.device("cuda")
+    for decay, boost in ((phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3), None),
+                         (D.to_gen(D.kstar_gamma_desc("gauss")), None),
+                         (phasespace.nbody_decay(B0_MASS, [PION_MASS] * 4), True)):
+        comp = decay.compile()
+        b = None
+        if boost:
+            p = torch.randn((n, 3), dtype=torch.float64, device=dev) * 3000.0
+            b = torch.cat([p, torch.sqrt((p * p).sum(1, keepdim=True) + B0_MASS**2)], dim=1).contiguous()
+        stats = torch.zeros((4,), dtype=torch.float64, device=dev)
+        w, w_max, _, _ = comp.launch(n, seed=5, boost_to=b, normalize_weights=False, stats=stats)
+        s = stats.cpu().numpy()
+        assert s[0] == float(w.max())
+        np.testing.assert_allclose(s[1], float(w.sum()), rtol=1e-12)
+        np.testing.assert_allclose(s[2], float((w * w).sum()), rtol=1e-12)
+        if b is None:
+            assert s[3] == float(w_max.max())  # event-independent maximum weight: reported exactly
+        else:
+            np.testing.assert_allclose(s[3], float(w_max.max()), rtol=1e-14)
