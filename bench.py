@@ -112,6 +112,26 @@ def _physical_gpu_index(local_rank):
     return local_rank
 
 
+def _bind_to_gpu_numa_node(gpu_index):
+    """Restrict this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the
+    end-to-end path (first touch) and the copy-engine traffic stay on the GPU's own NUMA node.  With several ranks
+    writing 56 GB/s each into host memory, remote-node buffers are what limits the aggregate."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------------------- CPU legs
 def _cpu_baseline(min_seconds=10.0):
     """Oracle (numpy port of the reference) on all host cores, bounded sample. Returns the dict for JSON."""
@@ -182,6 +202,7 @@ def run_b200(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = _cpu_baseline()  # before CUDA is busy; worker processes are spawned, not forked
 
+    numa_cpus = _bind_to_gpu_numa_node(_physical_gpu_index(local_rank)) if world > 1 else None
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
@@ -277,6 +298,8 @@ def run_b200(args, rank, local_rank, world):
                "d2h_bytes_per_step": BYTES_PER_EVENT * e2e_n, "steps": e2e_steps, "events_per_gpu_per_step": e2e_n,
                "api": "GenParticle.generate_host -> ps_generate_host (chunked generate + async D2H into pinned host memory)",
                "checksum_w0": float(w_host[0])}
+        if numa_cpus:
+            e2e["host_buffers"] = f"each rank bound to the {numa_cpus} CPUs NVML reports as local to its GPU before allocating"
     # ---- supplementary: the GPU-consumer case through the public API -- events stay in HBM for a device-side
     # consumer (a fit on the same GPU); per step only a scalar metric (mean weight) is read back to the host
     e2e_device = None
