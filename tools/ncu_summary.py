@@ -17,7 +17,9 @@ want = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__regis
         'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
-        'l1tex__t_bytes_pipe_lsu_mem_global_op_st.sum', 'lts__t_bytes.sum']
+        'l1tex__t_bytes_pipe_lsu_mem_global_op_st.sum', 'lts__t_bytes.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
+        'smsp__sass_average_data_bytes_per_sector_mem_global_op_st.ratio', 'dram__bytes_write.sum.pct_of_peak_sustained_elapsed']
 out = {"kernels": []}
 for r in rows[2:]:
     out["kernels"].append({k: (r[hdr.index(k)] + ' ' + units[hdr.index(k)]).strip() for k in want if k in hdr})
