@@ -167,7 +167,8 @@ def relbw_cdf(x, m, gamma):
     """
     a, b = m * m, m * gamma
     rho = math.sqrt(a * a + b * b)
-    p, q = math.sqrt(0.5 * (rho + a)), math.sqrt(0.5 * (rho - a))
+    p = math.sqrt(0.5 * (rho + a))
+    q = b / (2.0 * p)  # = sqrt((rho - a) / 2) without the cancellation for narrow resonances
     c_atan, c_log = 1.0 / (4.0 * rho * q), 1.0 / (8.0 * rho * p)
     x2r = x * x + rho
     tpx = 2.0 * p * x
@@ -181,7 +182,8 @@ RELBW_LAST_STEP = 1e-9
 def _relbw_consts(m, gamma):
     a, b = m * m, m * gamma
     rho = math.sqrt(a * a + b * b)
-    p, q = math.sqrt(0.5 * (rho + a)), math.sqrt(0.5 * (rho - a))
+    p = math.sqrt(0.5 * (rho + a))
+    q = b / (2.0 * p)  # 2 p q = b: stable for width / mass down to anything representable
     return p, q, 1.0 / (4.0 * rho * q), 1.0 / (8.0 * rho * p)
 
 

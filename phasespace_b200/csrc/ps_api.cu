@@ -193,7 +193,9 @@ void host_sampler_constants(int kind, double mass, double width, double out[5]) 
     } else if (kind == PS_MASS_RELBW) {
         const double a = mass * mass, b = mass * width;
         const double rho = std::sqrt(a * a + b * b);
-        const double p = std::sqrt(0.5 * (rho + a)), q = std::sqrt(0.5 * (rho - a));
+        // p + i q = sqrt(a + i b): q from 2 p q = b, not from sqrt((rho - a) / 2), which cancels to zero for narrow
+        // resonances (width / mass < 1e-8, e.g. the D0 in a DecayLanguage chain with a tiny width tolerance)
+        const double p = std::sqrt(0.5 * (rho + a)), q = b / (2.0 * p);
         out[0] = p;
         out[1] = q;
         out[2] = 2.0 * p / q;

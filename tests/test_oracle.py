@@ -259,3 +259,17 @@ def test_oracle_matches_reference_source(case):
     scale = D.B0_MASS if ref["boost"] is None else float(np.max(ref["boost"][:, 3]))
     for k, name in enumerate(ref["names"]):
         assert np.max(np.abs(parts[name] - ref["particles"][k])) <= 1e-13 * scale, name
+
+
+@pytest.mark.parametrize("width", [1e-3, 1e-6, 1.6e-9])
+def test_relbw_narrow_resonance(width):
+    """width / mass below 1e-8 (a D0 with its physical width in a DecayLanguage chain): the quartic's roots p + i q must
+    come from 2 p q = m * width -- sqrt((rho - m^2) / 2) cancels to zero.  A narrow relativistic Breit-Wigner is a
+    Lorentzian of half width ``width / 2`` around the pole."""
+    n, m = 20001, 1864.84
+    u = (np.arange(n) + 0.5) / n
+    x = orc.sample_mass(orc.RELBW, m, width, np.full(n, 633.0), np.full(n, 5279.0), u)
+    assert np.all(np.diff(x) >= 0) and np.all(np.isfinite(x))
+    q25, q50, q75 = np.quantile(x, [0.25, 0.5, 0.75])
+    assert abs(q50 - m) < 1e-3 * width + 1e-12 * m
+    assert (q75 - q25) / width == pytest.approx(1.0, rel=2e-2)
