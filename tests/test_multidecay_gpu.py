@@ -34,6 +34,15 @@ def test_single_chain():
     events = decay_list[0]
     assert set(events.keys()) == {"K-", "pi+", "pi+ [0]", "pi0", "gamma", "gamma [0]"}
     assert all(len(p) == 100 for p in events.values())
+    # the pi0 is a relativistic Breit-Wigner with its physical width (7.8e-6 MeV, width/mass = 6e-8) at this tolerance:
+    # the two photons reconstruct it within a few widths of the pole (regression for the narrow-resonance constants)
+    (weights, decay_list) = container.generate(n_events=20_000, seed=2)
+    ev = decay_list[0]
+    gg = ev["gamma"] + ev["gamma [0]"]
+    m_gg = torch.sqrt(gg[:, 3] ** 2 - (gg[:, :3] ** 2).sum(1))
+    assert float((m_gg - 134.9768).abs().median()) < 1e-4
+    total = sum(ev[k] for k in ("K-", "pi+", "pi+ [0]", "gamma", "gamma [0]"))
+    assert float(total[:, :3].abs().max()) < 1e-8 and bool(torch.isfinite(weights[0]).all())
 
 
 @pytest.mark.parametrize("chain", ["pi0_4branches", "dplus_4grandbranches", "dstarplus_big_decay"])
