@@ -264,3 +264,34 @@ def test_debug_mode_matches_reference_source(case, exact):
     scale = D.B0_MASS if ref["boost"] is None else float(np.max(ref["boost"][:, 3]))
     for k, name in enumerate(ref["names"]):
         assert np.max(np.abs(_np(parts[name]) - ref["particles"][k])) <= TOL * scale, name
+
+
+def _leaf(name, mass):
+    return (name, mass, "fixed", 0.0, [])
+
+
+_EDGE_TREES = {
+    # massless products allow arbitrarily light subsystems: the boosts then amplify rounding by gamma (1e-9 here)
+    "three_massless": (D.flat_desc(3, top=100.0, masses=[0.0, 0.0, 0.0]), 2000, 1e-9),
+    "gev_units": (("B", 5.27958, "fixed", 0.0, [
+        ("K*", 0.89581, "relbw", 0.0474, [_leaf("K", 0.493677), _leaf("pi", 0.13957)]), _leaf("g", 0.0)]), 2000, 1e-12),
+    "sixteen_body": (D.flat_desc(16, top=20000.0, masses=[139.57] * 16), 1000, 1e-12),
+    "forty_body_max_slots": (D.flat_desc(40, top=60000.0, masses=[139.57] * 40), 200, 1e-12),
+    "depth_five_chain": (("A", 10000.0, "fixed", 0.0, [
+        ("B", 6000.0, "gauss", 100.0, [
+            ("C", 3500.0, "bw", 50.0, [
+                ("D", 2000.0, "relbw", 30.0, [
+                    ("E", 900.0, "fixed", 0.0, [_leaf("e1", 139.57), _leaf("e2", 493.677)]), _leaf("d2", 139.57)]),
+                _leaf("c2", 105.66)]),
+            _leaf("b2", 0.0)]),
+        _leaf("a2", 938.272)]), 2000, 1e-11),
+    "one_kev_above_threshold": (D.flat_desc(3, top=3 * D.PION_MASS + 1e-3, masses=[D.PION_MASS] * 3), 2000, 1e-12),
+}
+
+
+@pytest.mark.parametrize("name", list(_EDGE_TREES))
+def test_edge_trees(name):
+    """Shapes and scales off the beaten path (all but the last are NVRTC-compiled): massless products, GeV units, the
+    largest tree the parameter block holds, a depth-five chain through all three samplers, a decay at threshold."""
+    desc, n, tol = _EDGE_TREES[name]
+    _compare(desc, n, exact=False, use_rng=True, tol=tol, loose=1e-6)
