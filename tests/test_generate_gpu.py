@@ -208,6 +208,18 @@ def test_generate_host_matches_device():
     hw, hwmax, hp = chain.generate_host(50_000, seed=2, normalize_weights=False, chunk_events=8192)
     assert np.array_equal(_np(w), hw) and np.array_equal(_np(wmax), hwmax)
     assert all(np.array_equal(_np(p[k]), hp[k]) for k in p)
+    # host-side boost_to (the H2D leg): per-event rows across chunk boundaries, and one broadcast row
+    four = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 4)
+    n = 70_001
+    rng = np.random.default_rng(4)
+    mom = rng.normal(0.0, 8000.0, (n, 3))
+    boost = np.concatenate([mom, np.sqrt((mom * mom).sum(1, keepdims=True) + B0_MASS**2)], axis=1)
+    for b in (boost, boost[:1]):
+        w, p = four.generate(n, boost_to=torch.as_tensor(b), seed=6)
+        hw, hp = four.generate_host(n, boost_to=b, seed=6, chunk_events=16384)
+        assert np.array_equal(_np(w), hw) and all(np.array_equal(_np(p[k]), hp[k]) for k in p)
+    with pytest.raises(ValueError):
+        four.generate_host(n, boost_to=boost[:5], seed=6)
 
 
 def test_kinematics_helpers():
