@@ -381,3 +381,36 @@ def test_kernel_epilogue_statistics(n):
             assert s[3] == float(w_max.max())  # event-independent maximum weight: reported exactly
         else:
             np.testing.assert_allclose(s[3], float(w_max.max()), rtol=1e-14)
+
+
+def test_threaded_generation():
+    """Four host threads drive the library at once (registry, JIT, error state and the host arena are shared): every
+    thread gets exactly the events a single thread gets."""
+    import threading
+
+    def work(k):
+        decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * (3 + k))  # 3..6 bodies
+        chain = D.to_gen(D.kstar_gamma_desc(["fixed", "gauss", "bw", "relbw"][k]))
+        out = []
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            for rep in range(5):
+                w, p = decay.generate(20_000, seed=100 + k)
+                cw, cp = chain.generate(20_000, seed=200 + k)
+                hw, hp = decay.generate_host(20_000, seed=100 + k, chunk_events=4096)
+                out.append((w.cpu(), p["p_0"].cpu(), cw.cpu(), cp["K+"].cpu(), torch.as_tensor(hw.copy())))
+        stream.synchronize()
+        return out
+
+    expected = [work(k) for k in range(4)]
+    results = [None] * 4
+    threads = [threading.Thread(target=lambda k=k: results.__setitem__(k, work(k))) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k in range(4):
+        assert results[k] is not None
+        for got, want in zip(results[k], expected[k]):
+            assert all(torch.equal(a, b) for a, b in zip(got, want))
+            assert torch.equal(got[0], got[4])  # generate_host delivers the same weights
