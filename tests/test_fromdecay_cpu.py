@@ -110,3 +110,31 @@ def test_unique_names():
 
     seen = set()
     assert [_unique_name("pi+", seen) for _ in range(4)] == ["pi+", "pi+ [0]", "pi+ [1]", "pi+ [2]"]
+
+
+def _describe(part):
+    fixed = bool(part.has_fixed_mass)
+    mass = float(part._mass_val) if fixed else part._mass.__name__
+    return {"name": part.name, "fixed": fixed, "mass": mass, "children": [_describe(c) for c in part.children]}
+
+
+def _load_reference_fromdecay():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_fromdecay.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_from_dict_matches_the_reference_implementation(case):
+    """tests/golden/reference_fromdecay.json holds what the reference's OWN from_dict / _recursively_traverse /
+    _unique_name (run unmodified through stand-ins, tests/golden/make_reference_fromdecay.py) builds for these chains:
+    same decay modes in the same order, same probabilities, same particle names ("pi+ [0]"), same fixed/resonant split
+    under the width tolerance, same mass-function choice (zfit key > particle_model_map > default)."""
+    ref = _load_reference_fromdecay()[case]
+    multi = GenMultiDecay.from_dict(getattr(example_decay_chains, ref["chain"]), **ref["kwargs"])
+    assert len(multi.gen_particles) == len(ref["modes"])
+    for (prob, part), want in zip(multi.gen_particles, ref["modes"]):
+        assert float(prob) == pytest.approx(want["probability"], rel=1e-12)
+        assert _describe(part) == want["tree"]
