@@ -304,8 +304,9 @@ def run_b200(args, rank, local_rank, world):
     # consumer (a fit on the same GPU); per step only a scalar metric (mean weight) is read back to the host
     e2e_device = None
     if not args.no_e2e:
-        for _ in range(2):  # warm-up: the caching allocator ends up holding the output slab
+        for _ in range(2):  # warm-up: the allocator ends up holding the output slab, torch has loaded its reduction
             w_dev, parts_dev = decay.generate(n, seed=args.seed)
+            float(w_dev.mean().item())
             del w_dev, parts_dev
         barrier()
         dev_steps = max(1, min(args.steps, 10))
