@@ -414,3 +414,35 @@ def test_threaded_generation():
         for got, want in zip(results[k], expected[k]):
             assert all(torch.equal(a, b) for a, b in zip(got, want))
             assert torch.equal(got[0], got[4])  # generate_host delivers the same weights
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_two_devices():
+    """One process drives two GPUs (threading): the same tree, AOT and JIT kernels, the host arena and the
+    histogram consumer on either device give identical events; two halves of an index range, one per device, concatenate
+    to the single-device result."""
+    from phasespace_b200.histogram import generate_histograms
+
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    jit = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 11)
+    chain = D.to_gen(D.kstar_gamma_desc("relbw"))
+    n = 100_000
+    results = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            w, p = decay.generate(n, seed=9)
+            jw, jp = jit.generate(2000, seed=9)
+            cw, cp = chain.generate(n, seed=9)
+            hw, hp = decay.generate_host(n, seed=9, chunk_events=16384)
+            hist, hist_w = generate_histograms(decay, n, seed=9, normalize=False, w_cap=1.0)
+            assert w.device.index == dev and cp["K+"].device.index == dev and hist_w.device.index == dev
+            results.append((w.cpu(), p["p_2"].cpu(), jw.cpu(), jp["p_10"].cpu(), cw.cpu(), cp["K+"].cpu(),
+                            torch.as_tensor(hw.copy()), hist_w.cpu(), hist["p_0"].cpu()))
+    for a, b in zip(*results):
+        assert torch.equal(a, b) if a.dtype != torch.float64 or a.ndim < 2 or a.shape[0] != 4 else torch.allclose(a, b, rtol=1e-12)
+    comp = decay.compile()
+    with torch.cuda.device(0):
+        w0, _, s0, _ = comp.launch(n // 2, seed=9, first_event=0)
+    with torch.cuda.device(1):
+        w1, _, s1, _ = comp.launch(n - n // 2, seed=9, first_event=n // 2)
+    assert torch.equal(torch.cat([w0.cpu(), w1.cpu()]), results[0][0])
