@@ -25,12 +25,31 @@ from .random import SeedLike, get_rng
 __all__ = ["GenParticle", "nbody_decay", "to_vectors", "ForbiddenDecayError", "CompiledDecay"]
 
 
+_CUDA_CHECKED = False
+_DEVICES: dict = {}
+
+
 def _device() -> torch.device:
-    if not torch.cuda.is_available():
-        raise RuntimeError(
-            "phasespace_b200 needs a CUDA device (B200, sm_100a): there is no CPU implementation of the generator."
-        )
-    return torch.device("cuda", torch.cuda.current_device())
+    """The current CUDA device.  (torch.cuda.is_available() costs microseconds per call: asked once per process.)"""
+    global _CUDA_CHECKED
+    if not _CUDA_CHECKED:
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "phasespace_b200 needs a CUDA device (B200, sm_100a): there is no CPU implementation of the generator."
+            )
+        _CUDA_CHECKED = True
+    index = torch.cuda.current_device()
+    dev = _DEVICES.get(index)
+    if dev is None:
+        dev = _DEVICES[index] = torch.device("cuda", index)
+    return dev
+
+
+try:  # the raw cudaStream_t of torch's current stream without building a Stream object (what Triton's launcher uses)
+    _raw_current_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover
+    def _raw_current_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
 
 
 def process_list_to_tensor(lst, device=None):
@@ -190,7 +209,7 @@ class CompiledDecay:
                 boost_to = boost_to.clone()
         flags = (_lib.PS_GEN_NORMALIZE if normalize_weights else 0) | (_lib.PS_GEN_EXACT if exact else 0)
         if stream is None:
-            stream = torch.cuda.current_stream(device).cuda_stream
+            stream = _raw_current_stream(device.index)
         stride = particles.stride(0) if self.n_particles > 1 and n > 0 else 4 * max(n, 1)
         rc = _lib.lib.ps_generate(
             self.handle, int(seed) & (2**64 - 1), int(first_event), n, _ptr(boost_to), boost_rows,
