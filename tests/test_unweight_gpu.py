@@ -57,3 +57,24 @@ def test_unweighted_chain():
     assert 0 < len(index) < 40_000 and torch.all(weights <= 1)
     w_all, _ = chain.generate(40_000, seed=8)
     assert torch.equal(weights, w_all[index])
+
+
+@pytest.mark.parametrize("n", [0, 1, 2048 * 256, 2048 * 256 + 1, 1_300_003])
+def test_multi_segment_scan(n):
+    """The tile-count scan works in segments of 2048 tiles (524288 events): sizes of zero, one, exactly one segment,
+    one event more, and two and a half segments, against the accept rule applied to the plain generator's weights."""
+    seed, w_bound = 23, 0.5
+    decay = phasespace.nbody_decay(D.B0_MASS, [D.PION_MASS] * 3)
+    parts, index, weights = generate_unweighted(decay, n, seed, w_bound=w_bound)
+    if n == 0:
+        assert index.numel() == 0 and weights.numel() == 0
+        return
+    w_all, p_all = decay.generate(n, seed=seed)
+    u = torch.as_tensor(uniform_table(seed, 0, n, 1, stream=1)[:, 0], device=w_all.device)
+    decided = (u * w_bound - w_all).abs() > 1e-12  # events decided by rounding are not compared
+    expect = u * w_bound < w_all
+    got = torch.zeros(n, dtype=torch.bool, device=w_all.device)
+    got[index] = True
+    assert bool((index[1:] > index[:-1]).all())
+    assert torch.equal(got[decided], expect[decided])
+    assert torch.equal(weights, w_all[index]) and torch.equal(parts["p_1"], p_all["p_1"][index])
