@@ -76,3 +76,21 @@ def test_sharded_histograms_single_process_and_ranges():
     assert torch.equal(wa + wb, w)
     for k in parts:
         np.testing.assert_allclose((pa[k] + pb[k]).cpu().numpy(), parts[k].cpu().numpy(), rtol=1e-11)
+
+
+def test_histogram_folds_and_single_bin():
+    """Enough events per CTA for several fixed-point folds (one every 16 tiles), and the worst case for the 32-bit
+    limbs: a single bin that takes every event of every tile."""
+    decay = phasespace.nbody_decay(D.B0_MASS, [D.PION_MASS] * 3)
+    n, seed = 3_000_000, 31
+    weights, parts = decay.generate(n, seed=seed)
+    ref_parts, ref_w = _reference_recipe(weights, parts)
+    got_parts, got_w = generate_histograms(decay, n, seed=seed)
+    for name in parts:
+        np.testing.assert_allclose(got_parts[name].cpu().numpy(), ref_parts[name], rtol=1e-9, atol=1e-15, err_msg=name)
+    np.testing.assert_allclose(got_w.cpu().numpy(), ref_w, rtol=1e-12, atol=0)
+    one_parts, one_w = generate_histograms(decay, n, seed=seed, bins=1, normalize=False)
+    assert float(one_w[0]) == n
+    total = float(weights.sum())
+    for name in parts:  # |p| < 3000 and 0 <= E < 3000 for every pion of a B0 decay: each row holds the sum of all weights
+        np.testing.assert_allclose(one_parts[name].cpu().numpy()[:, 0], total, rtol=1e-12)
