@@ -446,3 +446,19 @@ def test_one_process_two_devices():
     with torch.cuda.device(1):
         w1, _, s1, _ = comp.launch(n - n // 2, seed=9, first_event=n // 2)
     assert torch.equal(torch.cat([w0.cpu(), w1.cpu()]), results[0][0])
+
+
+@pytest.mark.parametrize("which", ["two_body", "kstar_gamma"])
+def test_covering_grid_with_several_tiles_per_cta(which):
+    """Memory-bound trees use the covering grid, where a CTA owns K consecutive tiles (K = 4..16 once the launch is
+    large enough): an odd event count that leaves the last CTA a partial chunk, compared piecewise with small launches
+    (K = 1) of the same index ranges."""
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS, D.KAON_MASS]) if which == "two_body" else D.to_gen(D.kstar_gamma_desc("bw"))
+    n, seed = 5_000_003, 12
+    comp = decay.compile()
+    w, _, slab, _ = comp.launch(n, seed)
+    assert bool(torch.isfinite(w).all())
+    for first, count in ((0, 70_001), (2_499_871, 99_999), (n - 65_537, 65_537)):
+        wp, _, sp, _ = comp.launch(count, seed, first_event=first)
+        assert torch.equal(wp, w[first:first + count])
+        assert torch.equal(sp, slab[:, first:first + count])
