@@ -220,6 +220,11 @@ def test_generate_host_matches_device():
         assert np.array_equal(_np(w), hw) and all(np.array_equal(_np(p[k]), hp[k]) for k in p)
     with pytest.raises(ValueError):
         four.generate_host(n, boost_to=boost[:5], seed=6)
+    # the staging arena grows when a later call asks for larger chunks (and for more particles per event)
+    ten = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 10)
+    w, p = ten.generate(300_000, seed=7)
+    hw, hp = ten.generate_host(300_000, seed=7, chunk_events=1 << 18)
+    assert np.array_equal(_np(w), hw) and all(np.array_equal(_np(p[k]), hp[k]) for k in p)
 
 
 def test_kinematics_helpers():
