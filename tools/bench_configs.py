@@ -61,6 +61,18 @@ for kind, fac in (("relbw", mf.relativistic_breitwigner_factory), ("gauss", mf.g
         ps.GenParticle("K*0", 895.81 if fac is None else fac(895.81, 47.4)).set_children(ps.GenParticle("K+", K), ps.GenParticle("pi-", PI)),
         ps.GenParticle("gamma", 0.0))
     run(f"4: B0->K*0(->K pi) gamma, {kind} K*0, n=1e8", chain, n8)
+# config 4 as BASELINE.json words it: through GenMultiDecay (public API: allocates its outputs, one host check per call)
+from phasespace_b200.fromdecay import GenMultiDecay
+kst = ps.GenParticle("B0", B0).set_children(
+    ps.GenParticle("K*0", mf.relativistic_breitwigner_factory(895.81, 47.4)).set_children(ps.GenParticle("K+", K), ps.GenParticle("pi-", PI)),
+    ps.GenParticle("gamma", 0.0))
+multi = GenMultiDecay([(1.0, kst)])
+def _multi():
+    w, ev = multi.generate(n8, seed=1)
+    del w, ev
+ms = timed(_multi, reps=5)
+print(json.dumps({"config": "4m: the same chain through GenMultiDecay([(1.0, tree)]).generate (API call, outputs allocated per call)",
+                  "n_events": n8, "ms": ms, "events_per_s": n8 / ms * 1e3}), flush=True)
 ten = ps.nbody_decay(B0, [PI] * 10)
 run("5a: 10-body, all events stored, n=5e7", ten, int(5e7 * scale))
 n5 = int(2.5e8 * scale)
