@@ -51,7 +51,7 @@ def _load():
         "ps_generate": (c.c_int, [vp, u64, u64, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, u32, vp]),
         "ps_generate_indexed": (c.c_int, [vp, u64, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, u32, vp]),
         "ps_generate_host": (c.c_int, [vp, u64, u64, i64, vp, i64, vp, vp, vp, i64, u32]),
-        "ps_unweight_mask": (c.c_int, [vp, u64, u64, i64, dbl, vp, vp, vp, u32, vp]),
+        "ps_unweight_mask": (c.c_int, [vp, u64, u64, i64, dbl, vp, vp, u32, vp]),
         "ps_unweight_scan": (c.c_int, [vp, i64, vp, vp, vp]),
         "ps_unweight_index": (c.c_int, [vp, vp, u64, i64, vp, vp]),
         "ps_histogram": (c.c_int, [vp, u64, u64, i64, vp, i64, i32, dbl, dbl, dbl, dbl, dbl, vp, vp, u32, vp]),

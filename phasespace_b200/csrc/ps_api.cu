@@ -519,8 +519,8 @@ int jit_compile(const KernelKey& key, const void** fn_out) {
         src += "extern \"C\" __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) ps_jit_kernel(const __grid_constant__ PsParams prm, const __grid_constant__ psk::PsHistParams h) {\n"
                "  psk::genbod_hist_body<" + key.sig + ", " + (key.boost ? "true" : "false") + ">(prm, h);\n}\n";
     } else {
-        src += "extern \"C\" __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) ps_jit_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask, int* tile_counts) {\n"
-               "  psk::genbod_mask_body<" + key.sig + ", " + (key.boost ? "true" : "false") + ">(prm, w_bound, mask, tile_counts);\n}\n";
+        src += "extern \"C\" __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) ps_jit_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask) {\n"
+               "  psk::genbod_mask_body<" + key.sig + ", " + (key.boost ? "true" : "false") + ">(prm, w_bound, mask);\n}\n";
     }
     std::vector<const char*> hdr_text, hdr_name;
     for (const EmbeddedHeader* h = kEmbeddedHeaders; h->name; ++h) {
@@ -806,13 +806,29 @@ extern "C" int ps_generate_host(const ps_tree* tree, uint64_t seed, uint64_t fir
 // ---------------------------------------------------------------------------------- unweighting
 namespace {
 
-// Exclusive scan of int32 tile counts into int64 offsets, three small kernels over segments of PS_SCAN_SEG tiles:
+// Exclusive scan of the accepted-event counts per tile of PS_BLOCK events into int64 offsets.  A tile's count is the
+// population count of its eight mask words (tile_count), so the mask pass needs no CTA-wide reduction.  Three small
+// kernels over segments of PS_SCAN_SEG tiles:
 //   1. every CTA sums its segment (coalesced loads) and parks the sum in offsets[first tile of the segment];
 //   2. one CTA scans those parked sums in place (exclusive) and writes the grand total;
 //   3. every CTA reads its segment's offset, scans its counts in shared memory and writes the final offsets
 //      (the first tile of a segment gets exactly the value parked there, so no scratch buffer is needed).
 #define PS_SCAN_SEG 2048
 #define PS_SCAN_THREADS 256
+static_assert(PS_BLOCK == 256, "tile_count reads the eight mask words of a tile as two 16-byte vectors");
+
+// accepted events in tile `tile`: mask holds n_words words (16-byte aligned), one bit per event
+__device__ __forceinline__ int tile_count(const unsigned int* mask, long long tile, long long n_words) {
+    const long long w0 = tile * (PS_BLOCK / 32);
+    if (w0 + 8 <= n_words) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(mask + w0));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(mask + w0 + 4));
+        return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+    }
+    int c = 0;
+    for (long long w = w0; w < n_words; ++w) c += __popc(mask[w]);
+    return c;
+}
 
 __device__ __forceinline__ long long block_exclusive_scan(long long v, long long* warp_sums, long long* block_total) {
     // exclusive scan of one value per thread over a CTA of PS_SCAN_THREADS threads (or 1024 in phase 2)
@@ -842,7 +858,8 @@ __device__ __forceinline__ long long block_exclusive_scan(long long v, long long
     return out;
 }
 
-__global__ void __launch_bounds__(PS_SCAN_THREADS) scan_phase1_kernel(const int* counts, long long n, long long* offsets) {
+__global__ void __launch_bounds__(PS_SCAN_THREADS) scan_phase1_kernel(const unsigned int* mask, long long n_words, long long n,
+                                                                      long long* offsets) {
     __shared__ long long warp_sums[32];
     __shared__ long long total;
     const long long base = (long long)blockIdx.x * PS_SCAN_SEG;
@@ -850,7 +867,7 @@ __global__ void __launch_bounds__(PS_SCAN_THREADS) scan_phase1_kernel(const int*
 #pragma unroll
     for (int k = 0; k < PS_SCAN_SEG / PS_SCAN_THREADS; ++k) {
         const long long i = base + k * PS_SCAN_THREADS + threadIdx.x;
-        if (i < n) s += counts[i];
+        if (i < n) s += tile_count(mask, i, n_words);
     }
     (void)block_exclusive_scan(s, warp_sums, &total);
     if (threadIdx.x == 0) offsets[base] = total;
@@ -871,7 +888,8 @@ __global__ void __launch_bounds__(1024) scan_phase2_kernel(long long* offsets, l
     if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 
-__global__ void __launch_bounds__(PS_SCAN_THREADS) scan_phase3_kernel(const int* counts, long long n, long long* offsets) {
+__global__ void __launch_bounds__(PS_SCAN_THREADS) scan_phase3_kernel(const unsigned int* mask, long long n_words, long long n,
+                                                                      long long* offsets) {
     __shared__ int seg_counts[PS_SCAN_SEG];
     __shared__ long long warp_sums[32];
     __shared__ long long total;
@@ -881,7 +899,7 @@ __global__ void __launch_bounds__(PS_SCAN_THREADS) scan_phase3_kernel(const int*
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         const long long i = base + k * PS_SCAN_THREADS + threadIdx.x;
-        seg_counts[k * PS_SCAN_THREADS + threadIdx.x] = i < n ? counts[i] : 0;
+        seg_counts[k * PS_SCAN_THREADS + threadIdx.x] = i < n ? tile_count(mask, i, n_words) : 0;
     }
     __syncthreads();  // also orders the read of offsets[base] before thread 0 overwrites it below
     long long mine = 0;
@@ -896,23 +914,33 @@ __global__ void __launch_bounds__(PS_SCAN_THREADS) scan_phase3_kernel(const int*
     }
 }
 
-// one warp per 32 events: accepted events write their global index at the scanned position
+// One thread per mask word (32 events): its first output position is the tile's offset plus the accepted events of the
+// preceding words of the tile (prefix sum over the eight lanes that share a tile); it then writes the global index of
+// each set bit.  One word per thread keeps a few hundred thousand independent loads in flight -- a CTA per tile with one
+// dependent load chain per iteration was latency-bound (0.69 ms per 1.3e8 candidates).
 __global__ void __launch_bounds__(PS_BLOCK) index_kernel(const unsigned int* mask, const long long* tile_offsets,
-                                                         unsigned long long first_event, long long n, long long* out) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (long long tile = blockIdx.x; tile * PS_BLOCK < n; tile += gridDim.x) {
-        const long long w0 = tile * (PS_BLOCK / 32);
-        long long base = tile_offsets[tile];
-        unsigned int word = 0;
+                                                         unsigned long long first_event, long long n_words, long long* out) {
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * PS_BLOCK;
+    // the loop bound is rounded up to whole warps: the shuffles below need every lane
+    for (long long w0 = (long long)blockIdx.x * PS_BLOCK + (threadIdx.x - lane); w0 < n_words; w0 += stride) {
+        const long long w = w0 + lane;
+        unsigned int word = w < n_words ? __ldg(mask + w) : 0u;
+        const int c = __popc(word);
+        int incl = c;
 #pragma unroll
-        for (int k = 0; k < PS_BLOCK / 32; ++k) {
-            const unsigned int wk = ((w0 + k) * 32 < n) ? mask[w0 + k] : 0u;
-            if (k < wid) base += __popc(wk);
-            if (k == wid) word = wk;
+        for (int o = 1; o < PS_BLOCK / 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o, PS_BLOCK / 32);
+            if ((lane & (PS_BLOCK / 32 - 1)) >= o) incl += up;
         }
-        if (word & (1u << lane)) {
-            const long long i = tile * PS_BLOCK + threadIdx.x;
-            out[base + __popc(word & ((1u << lane) - 1u))] = (long long)(first_event + (unsigned long long)i);
+        if (word) {
+            long long pos = __ldg(tile_offsets + w / (PS_BLOCK / 32)) + (incl - c);
+            const unsigned long long ev0 = first_event + (unsigned long long)w * 32ull;
+            while (word) {
+                const int bit = __ffs(word) - 1;
+                word &= word - 1u;
+                out[pos++] = (long long)(ev0 + (unsigned long long)bit);
+            }
         }
     }
 }
@@ -920,8 +948,8 @@ __global__ void __launch_bounds__(PS_BLOCK) index_kernel(const unsigned int* mas
 }  // namespace
 
 extern "C" int ps_unweight_mask(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events, double w_bound,
-                                uint32_t* mask, int32_t* tile_counts, int32_t* err_flag, uint32_t flags, void* stream) {
-    if (!tree || !mask || !tile_counts) return fail(PS_E_INVALID, "null argument");
+                                uint32_t* mask, int32_t* err_flag, uint32_t flags, void* stream) {
+    if (!tree || !mask) return fail(PS_E_INVALID, "null argument");
     if (tree->n_user > 0) return fail(PS_E_INVALID, "unweighting does not take user-mass trees");
     if (!(w_bound > 0.0)) return fail(PS_E_INVALID, "w_bound must be > 0");
     PsParams p;
@@ -937,19 +965,21 @@ extern "C" int ps_unweight_mask(const ps_tree* tree, uint64_t seed, uint64_t fir
     PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
     int grid = (int)((long long)sms * 8 < tiles ? (long long)sms * 8 : tiles);
-    void* args[] = {&p, &w_bound, &mask, &tile_counts};
+    void* args[] = {&p, &w_bound, &mask};
     PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, 0, (cudaStream_t)stream));
     g_launches.fetch_add(1);
     return 0;
 }
 
-extern "C" int ps_unweight_scan(const int32_t* tile_counts, int64_t n_tiles, int64_t* tile_offsets, int64_t* total, void* stream) {
-    if (!tile_counts || !tile_offsets || n_tiles < 0) return fail(PS_E_INVALID, "null argument");
+extern "C" int ps_unweight_scan(const uint32_t* mask, int64_t n_events, int64_t* tile_offsets, int64_t* total, void* stream) {
+    if (!mask || !tile_offsets || n_events < 0) return fail(PS_E_INVALID, "null argument");
+    if (reinterpret_cast<uintptr_t>(mask) & 15u) return fail(PS_E_INVALID, "mask must be 16-byte aligned");
+    const long long n_words = (n_events + 31) / 32, n_tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
     const long long n_segments = (n_tiles + PS_SCAN_SEG - 1) / PS_SCAN_SEG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_segments > 0) scan_phase1_kernel<<<(unsigned)n_segments, PS_SCAN_THREADS, 0, st>>>(tile_counts, n_tiles, (long long*)tile_offsets);
+    if (n_segments > 0) scan_phase1_kernel<<<(unsigned)n_segments, PS_SCAN_THREADS, 0, st>>>(mask, n_words, n_tiles, (long long*)tile_offsets);
     scan_phase2_kernel<<<1, 1024, 0, st>>>((long long*)tile_offsets, n_segments, (long long*)total);
-    if (n_segments > 0) scan_phase3_kernel<<<(unsigned)n_segments, PS_SCAN_THREADS, 0, st>>>(tile_counts, n_tiles, (long long*)tile_offsets);
+    if (n_segments > 0) scan_phase3_kernel<<<(unsigned)n_segments, PS_SCAN_THREADS, 0, st>>>(mask, n_words, n_tiles, (long long*)tile_offsets);
     PS_CUDA(cudaGetLastError());
     g_launches.fetch_add(n_segments > 0 ? 3 : 1);
     return 0;
@@ -962,9 +992,10 @@ extern "C" int ps_unweight_index(const uint32_t* mask, const int64_t* tile_offse
     int dev = 0, sms = 0;
     PS_CUDA(cudaGetDevice(&dev));
     PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
-    long long grid = (long long)sms * 8 < tiles ? (long long)sms * 8 : tiles;
-    index_kernel<<<(int)grid, PS_BLOCK, 0, (cudaStream_t)stream>>>(mask, (const long long*)tile_offsets, first_event, n_events, (long long*)event_index);
+    const long long n_words = (n_events + 31) / 32;
+    const long long ctas = (n_words + PS_BLOCK - 1) / PS_BLOCK;
+    const long long grid = (long long)sms * 8 < ctas ? (long long)sms * 8 : ctas;
+    index_kernel<<<(int)grid, PS_BLOCK, 0, (cudaStream_t)stream>>>(mask, (const long long*)tile_offsets, first_event, n_words, (long long*)event_index);
     PS_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     return 0;

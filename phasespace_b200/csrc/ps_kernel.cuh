@@ -213,12 +213,16 @@ __device__ __forceinline__ void lorentz_boost_exact(double& x, double& y, double
     e = gamma * (e + bp);
 }
 
+// One compare and four 32-bit selects.  (fmin / fmax cost fourteen instructions per exchange on sm_100a: there is no
+// fp64 min/max instruction, and their NaN handling compiles to DSETP.MIN/MAX + SEL + FSEL + eight register moves.
+// The sorted values are uniforms, never NaN.)
 __device__ __forceinline__ void cmp_exchange(double& a, double& b) {
-    const double lo = fmin(a, b), hi = fmax(a, b);
+    const bool swap = b < a;
+    const double lo = swap ? b : a, hi = swap ? a : b;
     a = lo, b = hi;
 }
 // Sorting networks: optimal (fewest comparators) up to 8 elements -- 1, 3, 5, 9, 12, 16, 19 instead of the K(K-1)/2
-// of insertion order; a compare-exchange of doubles is five instructions on sm_100a (no fp64 min/max).
+// of insertion order.
 template <int K>
 __device__ __forceinline__ void sort_network(double (&r)[K]) {
 #define PS_CE(i, j) cmp_exchange(r[i], r[j])
@@ -747,13 +751,13 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
             prm.weights[i] = w_out;
             store_particles(c, prm.particles + i * 4, prm.particle_stride, MakeSeq<P>{});
             bad_any |= c.bad;
-            st_max = fmax(st_max, w_out);
+            st_max = w_out > st_max ? w_out : st_max;  // (fmax / fmin: seven instructions each on sm_100a, see cmp_exchange)
             st_sum += w_out;
             st_sum2 += w_out * w_out;
 #if PS_EXACT
-            st_wmax = fmax(st_wmax, w_max);
+            st_wmax = w_max > st_wmax ? w_max : st_wmax;
 #else
-            st_inv_min = fmin(st_inv_min, inv_w_max);  // max w_max = 1 / min (1 / w_max)
+            st_inv_min = inv_w_max < st_inv_min ? inv_w_max : st_inv_min;  // max w_max = 1 / min (1 / w_max)
 #endif
         }
         }
@@ -806,16 +810,16 @@ __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) genbod_kernel(const _
 // ------------------------------------------------------------------ unweighting, pass 1
 // Recomputes the event weights only (the rotations, boosts and their draws are dead code here and
 // are eliminated), draws one acceptance uniform per event from Philox stream 1 and records
-// accept = (u * w_bound < w / w_max) as one bit per event plus a per-tile count.  Together with
+// accept = (u * w_bound < w / w_max) as one bit per event.  Together with
 // ps_unweight_scan / ps_unweight_index this yields the accepted events ordered by event index,
 // independent of grid size or GPU count; ps_generate_indexed then regenerates only those.
 template <class Tree, bool BOOST>
-__device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_bound, unsigned int* mask,
-                                                 int* tile_counts) {
+__device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_bound, unsigned int* mask) {
     constexpr int P = Tree::n_below;
-    __shared__ int warp_counts[PS_BLOCK / 32];
     const long long n = prm.n_events;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     bool bad_any = false;
+    // no CTA-wide synchronisation: the per-tile counts the scan needs are the population counts of the mask words
     for (long long tile = blockIdx.x; tile * PS_BLOCK < n; tile += gridDim.x) {
         const long long i = tile * PS_BLOCK + threadIdx.x;
         bool accept = false;
@@ -841,29 +845,17 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
             bad_any |= c.bad;
         }
         const unsigned int word = __ballot_sync(0xffffffffu, accept);
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        if (lane == 0) {
-            const long long wi = tile * (PS_BLOCK / 32) + wid;
-            if (wi * 32 < n) mask[wi] = word;
-            warp_counts[wid] = __popc(word);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int total = 0;
-#pragma unroll
-            for (int k = 0; k < PS_BLOCK / 32; ++k) total += warp_counts[k];
-            tile_counts[tile] = total;
-        }
-        __syncthreads();
+        const long long wi = tile * (PS_BLOCK / 32) + wid;
+        if (lane == 0 && wi * 32 < n) mask[wi] = word;
     }
     if (bad_any) *prm.err_flag = PS_ERR_FORBIDDEN;
 }
 
 template <class Tree, bool BOOST, int EXACT>
 __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS)
-    genbod_mask_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask, int* tile_counts) {
+    genbod_mask_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask) {
     static_assert(EXACT == PS_EXACT, "variant tag must match the translation unit");
-    genbod_mask_body<Tree, BOOST>(prm, w_bound, mask, tile_counts);
+    genbod_mask_body<Tree, BOOST>(prm, w_bound, mask);
 }
 
 // ------------------------------------------------------------------ fused weighted histograms

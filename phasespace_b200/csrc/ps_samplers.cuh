@@ -30,7 +30,11 @@ __device__ __forceinline__ SamplerConst sampler_const(const PsParams& prm, int s
     return SamplerConst{prm.mass[s1], prm.width[s1], prm.sc[0][s1], prm.sc[1][s1], prm.sc[2][s1], prm.sc[3][s1], prm.sc[4][s1]};
 }
 
-__device__ __forceinline__ double clamp_mass(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+// fmin(fmax(x, lo), hi) -- NaN maps to lo -- as two compares and selects (fmin / fmax are seven instructions each)
+__device__ __forceinline__ double clamp_mass(double x, double lo, double hi) {
+    const double y = x >= lo ? x : lo;
+    return y > hi ? hi : y;
+}
 
 // truncated normal(mu = m, sigma = w) on [lo, hi]
 template <bool CONST_LIM>

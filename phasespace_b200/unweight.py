@@ -5,8 +5,7 @@ The consumer of weighted phase-space events usually unweights them (accept event
 *generated* event; instead
 
 1. ``ps_unweight_mask``   recomputes only the weights (no 4-vectors are formed or stored), draws the
-                          acceptance uniform from Philox stream 1 and emits one bit per event plus a
-                          count per tile of 256 events,
+                          acceptance uniform from Philox stream 1 and emits one bit per event,
 2. ``ps_unweight_scan`` / ``ps_unweight_index``  turn that into the ordered list of accepted event indices,
 3. ``ps_generate_indexed`` regenerates exactly those events (the RNG is counter based) into a dense slab.
 
@@ -21,6 +20,8 @@ import torch
 
 from . import _lib
 from .phasespace import _device, _ptr
+
+_CAPACITY_STEP = 1 << 16  # events
 
 
 def generate_unweighted(decay, n_events: int, seed: int, *, w_bound: float = 1.0, first_event: int = 0,
@@ -42,26 +43,31 @@ def generate_unweighted(decay, n_events: int, seed: int, *, w_bound: float = 1.0
     stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     n_tiles = (n + _lib.TILE - 1) // _lib.TILE
     mask = torch.empty(((n + 31) // 32,), dtype=torch.int32, device=device)
-    counts = torch.empty((max(n_tiles, 1),), dtype=torch.int32, device=device)
     offsets = torch.empty((max(n_tiles, 1),), dtype=torch.int64, device=device)
-    total = torch.zeros((1,), dtype=torch.int64, device=device)
-    err = torch.zeros((1,), dtype=torch.int32, device=device)
+    # [accepted count (int64) | error flag (int32, low half of the second word)]: one read-back for both
+    state = torch.zeros((2,), dtype=torch.int64, device=device)
+    total, err = state[:1], state[1:].view(torch.int32)[:1]
     flags = _lib.PS_GEN_EXACT if exact else 0
     seed = int(seed) & (2**64 - 1)
     if n > 0:
         _lib.check(lib.ps_unweight_mask(compiled.handle, seed, int(first_event), n, float(w_bound), _ptr(mask),
-                                        _ptr(counts), _ptr(err), flags, stream))
-        _lib.check(lib.ps_unweight_scan(_ptr(counts), n_tiles, _ptr(offsets), _ptr(total), stream))
-    n_acc = int(total.item())
-    if int(err.item()):
+                                        _ptr(err), flags, stream))
+        _lib.check(lib.ps_unweight_scan(_ptr(mask), n, _ptr(offsets), _ptr(total), stream))
+    n_acc, failed = state.tolist()
+    if failed:
         raise _lib.ForbiddenDecayError("Forbidden decay")
-    index = torch.empty((n_acc,), dtype=torch.int64, device=device)
-    weights = torch.empty((n_acc,), dtype=torch.float64, device=device)
-    slab = torch.empty((compiled.n_particles, n_acc, 4), dtype=torch.float64, device=device)
+    # Capacity rounded up to a multiple of 65536 events: consecutive chunks of a long run accept slightly different
+    # numbers of events, and buffers of a size seen before come out of torch's caching allocator instead of cudaMalloc
+    # (which costs more than a millisecond for the 3 GB slab of a 10-body chunk).
+    cap = -(-n_acc // _CAPACITY_STEP) * _CAPACITY_STEP if n_acc > _CAPACITY_STEP else n_acc
+    index = torch.empty((cap,), dtype=torch.int64, device=device)[:n_acc]
+    weights = torch.empty((cap,), dtype=torch.float64, device=device)[:n_acc]
+    slab = torch.empty((compiled.n_particles, cap, 4), dtype=torch.float64, device=device)
     if n_acc > 0:
         _lib.check(lib.ps_unweight_index(_ptr(mask), _ptr(offsets), int(first_event), n, _ptr(index), stream))
         _lib.check(lib.ps_generate_indexed(
             compiled.handle, seed, _ptr(index), n_acc, None, 0, None, _ptr(weights), None, _ptr(slab),
-            int(4 * n_acc), None, _ptr(err), flags | _lib.PS_GEN_NORMALIZE, stream))
+            int(4 * max(cap, 1)), None, _ptr(err), flags | _lib.PS_GEN_NORMALIZE, stream))
+    slab = slab[:, :n_acc]
     parts = {name: slab[compiled.slots[name]] for name in compiled.names}
     return parts, index, weights
