@@ -125,30 +125,56 @@ struct Ctx {
     bool bad;
 
     // Draw number COL of this event: the 51-bit field at bit offset 51*COL of the event's Philox bit string
-    // (ps_philox.cuh).  Draws are consumed strictly in column order, so at most the block that holds the
-    // first bit and the one that holds the last bit are needed; which blocks are fresh is known at compile time.
+    // (ps_philox.cuh), as the two words of the double d = 1 + u/2 in [1, 1.5).  Draws are consumed strictly in column
+    // order, so at most the block that holds the first bit and the one that holds the last bit are needed; which
+    // blocks are fresh is known at compile time.
+    template <int COL>
+    __device__ __forceinline__ double mantissa() {
+        constexpr int bit0 = PS_UNIFORM_BITS * COL;
+        constexpr int FB = bit0 / 128, LB = (bit0 + PS_UNIFORM_BITS - 1) / 128;
+        constexpr int PREV = COL == 0 ? -1 : (bit0 - 1) / 128;  // last block touched by the previous column
+        if constexpr (FB > PREV) {
+            const Philox4 r = philox4x32_10(seed, event, FB, 0u);
+            w[0] = r.w[0], w[1] = r.w[1], w[2] = r.w[2], w[3] = r.w[3];
+        }
+        unsigned int x[8] = {w[0], w[1], w[2], w[3], 0u, 0u, 0u, 0u};
+        if constexpr (LB > FB) {
+            const Philox4 r = philox4x32_10(seed, event, LB, 0u);
+            x[4] = r.w[0], x[5] = r.w[1], x[6] = r.w[2], x[7] = r.w[3];
+            w[0] = r.w[0], w[1] = r.w[1], w[2] = r.w[2], w[3] = r.w[3];
+        }
+        unsigned int lo, hiword;
+        field_words<bit0 - 128 * FB>(x, lo, hiword);
+        return __hiloint2double((int)hiword, (int)lo);
+    }
+    // the uniform u = 2 d - 2 itself
     template <int COL>
     __device__ __forceinline__ double next() {
-        if constexpr (DBG) {
+        if constexpr (DBG)
             return dbg_row[COL];
+        else
+            return fma(mantissa<COL>(), 2.0, -2.0);
+    }
+    // 2 u - 1 (the cosine of a polar angle) = 4 d - 5: exact either way, one instruction from d
+    template <int COL>
+    __device__ __forceinline__ double next_cos() {
+        if constexpr (DBG || PS_EXACT)
+            return 2.0 * next<COL>() - 1.0;
+        else
+            return fma(mantissa<COL>(), 4.0, -5.0);
+    }
+    // the arguments of sincos_turn for the azimuth 2 pi u: y = 4 u + PS_TURN_MAGIC (one rounding of the same real number
+    // either way) and 2 u (exact)
+    template <int COL>
+    __device__ __forceinline__ void next_turn(double& y, double& u2) {
+        if constexpr (DBG) {
+            const double u = dbg_row[COL];
+            y = fma(u, 4.0, PS_TURN_MAGIC);
+            u2 = u + u;
         } else {
-            constexpr int bit0 = PS_UNIFORM_BITS * COL;
-            constexpr int FB = bit0 / 128, LB = (bit0 + PS_UNIFORM_BITS - 1) / 128;
-            constexpr int PREV = COL == 0 ? -1 : (bit0 - 1) / 128;  // last block touched by the previous column
-            if constexpr (FB > PREV) {
-                const Philox4 r = philox4x32_10(seed, event, FB, 0u);
-                w[0] = r.w[0], w[1] = r.w[1], w[2] = r.w[2], w[3] = r.w[3];
-            }
-            unsigned int x[8] = {w[0], w[1], w[2], w[3], 0u, 0u, 0u, 0u};
-            if constexpr (LB > FB) {
-                const Philox4 r = philox4x32_10(seed, event, LB, 0u);
-                x[4] = r.w[0], x[5] = r.w[1], x[6] = r.w[2], x[7] = r.w[3];
-                w[0] = r.w[0], w[1] = r.w[1], w[2] = r.w[2], w[3] = r.w[3];
-            }
-            constexpr int o = bit0 - 128 * FB, i = o / 32, sh = o % 32;
-            const unsigned int lo = sh ? __funnelshift_r(x[i], x[i + 1], sh) : x[i];
-            const unsigned int hi = sh ? __funnelshift_r(x[i + 1], x[i + 2], sh) : x[i + 1];
-            return uniform_from_bits(lo, hi);
+            const double d = mantissa<COL>();
+            y = fma(d, 8.0, PS_TURN_MAGIC - 8.0);
+            u2 = fma(d, 4.0, -4.0);
         }
     }
 };
@@ -336,12 +362,11 @@ __device__ __forceinline__ void genbod_step_exact(C& c, const double* pd, const 
 template <int N, int K, int AB, class C>
 __device__ __forceinline__ void genbod_step_fast(C& c, const double* pd, const double* ra, const double* enew,
                                                  const double* esub, double* x, double* y, double* z, double* e) {
-    const double ua = c.template next<AB>();
-    const double ub = c.template next<AB + 1>();
-    const double cz = 2.0 * ua - 1.0;
-    const double sz = sqrt_pos1(fma(-cz, cz, 1.0));
-    double sy, cy;
-    sincos_2pi(ub, sy, cy);
+    const double cz = c.template next_cos<AB>();
+    const double sz = sqrt_unit1(fma(-cz, cz, 1.0));
+    double ty, tu, sy, cy;
+    c.template next_turn<AB + 1>(ty, tu);
+    sincos_turn(ty, tu, sy, cy);
     const double t = sz * pd[K - 1];
     if constexpr (K == 1) {
         // particles 0 and 1 are back to back: (0, +-pd0, 0) rotated

@@ -57,9 +57,21 @@ __device__ __forceinline__ Philox4 philox4x32_10(unsigned long long seed, unsign
 }
 
 // 51 random bits (lo: 32, hi: low 19 bits used) -> U[0,1) with resolution 2^-51: the field fills the low
-// 51 mantissa bits of a double in [1, 1.5), and 2 d - 2 is exact.
+// 51 mantissa bits of a double d in [1, 1.5), and u = 2 d - 2 is exact.
 __device__ __forceinline__ double uniform_from_bits(unsigned int lo, unsigned int hi) {
     return fma(__hiloint2double((int)((hi & 0x7FFFFu) | 0x3FF00000u), (int)lo), 2.0, -2.0);
+}
+
+// The two words of that double d for the field at bit offset O (0..127) of the bit string x[0..7] (two consecutive
+// Philox blocks, or one block and zeros): lo = bits [O, O+32); hiword = exponent 0x3FF over bits [O+32, O+51).
+// (Sliding the 19 high bits under the exponent with a third funnel shift, __funnelshift_r(t, 0x7FE, 13), saves the
+// or, but measured no faster: the constant then occupies a register.)
+template <int O>
+__device__ __forceinline__ void field_words(const unsigned int* x, unsigned int& lo, unsigned int& hiword) {
+    constexpr int i = O / 32, sh = O % 32, j = (O + 19) / 32, s2 = (O + 19) % 32;
+    lo = sh ? __funnelshift_r(x[i], x[i + 1], sh) : x[i];
+    const unsigned int t = s2 ? __funnelshift_r(x[j], x[j + 1], s2) : x[j];  // the 19 high bits on top of a word
+    hiword = (t >> 13) | 0x3FF00000u;
 }
 
 // uniform number COL of an event in any stream (same bit layout as Ctx::next in ps_kernel.cuh, blocks recomputed
@@ -68,16 +80,15 @@ template <int COL>
 __device__ __forceinline__ double philox_uniform_col(unsigned long long seed, unsigned long long event, unsigned int stream) {
     constexpr int bit0 = PS_UNIFORM_BITS * COL;
     constexpr int FB = bit0 / 128, LB = (bit0 + PS_UNIFORM_BITS - 1) / 128;
-    constexpr int o = bit0 - 128 * FB, i = o / 32, sh = o % 32;
     const Philox4 a = philox4x32_10(seed, event, FB, stream);
     unsigned int x[8] = {a.w[0], a.w[1], a.w[2], a.w[3], 0u, 0u, 0u, 0u};
     if constexpr (LB > FB) {
         const Philox4 b = philox4x32_10(seed, event, LB, stream);
         x[4] = b.w[0], x[5] = b.w[1], x[6] = b.w[2], x[7] = b.w[3];
     }
-    const unsigned int lo = sh ? __funnelshift_r(x[i], x[i + 1], sh) : x[i];
-    const unsigned int hi = sh ? __funnelshift_r(x[i + 1], x[i + 2], sh) : x[i + 1];
-    return uniform_from_bits(lo, hi);
+    unsigned int lo, hiword;
+    field_words<bit0 - 128 * FB>(x, lo, hiword);
+    return fma(__hiloint2double((int)hiword, (int)lo), 2.0, -2.0);
 }
 
 // first uniform of block 0 of a stream (acceptance draws, stand-alone samplers)
