@@ -1,0 +1,52 @@
+#!/usr/bin/env python3
+"""profiles/<tag>_configs_ncu.json and the fp64 instruction counts of profiles/fp64_pipe.json from the ncu metrics pass of
+tools/profile_configs.sh:   python tools/configs_summary.py gpurun_out/profile_configs.csv r01_v6 [n_events]"""
+import csv, json, os, shutil, sys
+
+src, tag = sys.argv[1], sys.argv[2]
+n_events = int(float(sys.argv[3])) if len(sys.argv) > 3 else 20_000_000
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+CONFIGS = ["flat 2-body", "flat 3-body (headline)", "flat 4-body", "flat 6-body", "flat 10-body",
+           "flat 4-body + per-event boost_to", "K* gamma chain, fixed K*", "K* gamma chain, Cauchy K*",
+           "K* gamma chain, truncated-normal K*", "K* gamma chain, relativistic BW K*",
+           "3-body fused histograms (13 x 100 bins; native 32-bit shared atomics on fixed-point limbs)"]
+KEYS = ["flat_2body", "flat_3body", "flat_4body", "flat_6body", "flat_10body", "flat_4body_boost", "kstar_gamma_fixed",
+        "kstar_gamma_bw", "kstar_gamma_gauss", "kstar_gamma_relbw", None]
+rows = list(csv.DictReader(l for l in open(src) if l.startswith('"')))
+launches = {}
+for r in rows:
+    launches.setdefault(int(r["ID"]), {"kernel": r["Kernel Name"]})[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
+# generate_histograms() runs a small pilot generation before its fused kernel: keep the ten generator launches and
+# the histogram kernel (the last launch)
+ordered = [m for _, m in sorted(launches.items())]
+ordered = ordered[:len(CONFIGS) - 1] + [ordered[-1]]
+assert "hist" in ordered[-1]["kernel"] and len(ordered) == len(CONFIGS), len(launches)
+warp_events = n_events / 32
+out = {"what": f"ncu metrics pass over one launch of every generator kernel behind the BASELINE.json configs "
+               f"(tools/profile_configs.sh, ncu --clock-control none, {n_events:.0e} events per launch, one B200)",
+       "fp64_peak_warp_inst_per_clk_per_smsp": 0.458, "kernels": []}
+counts = {}
+for m, config, key in zip(ordered, CONFIGS, KEYS):
+    fp64 = m["smsp__inst_executed_pipe_fp64.sum"] / warp_events
+    out["kernels"].append({
+        "config": config, "kernel": m["kernel"][:160], "gpu_time_ms": round(m["gpu__time_duration.sum"] / 1e6, 4),
+        "warp_inst_per_warp_event": round(m["smsp__inst_executed.sum"] / warp_events, 1),
+        "fp64_warp_inst_per_warp_event": round(fp64, 1),
+        "fp64_pipe_pct_of_peak": round(m["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"], 1),
+        "issue_active_pct": round(m["smsp__issue_active.avg.pct_of_peak_sustained_active"], 1),
+        "xu_pipe_pct": round(m["sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"], 1),
+        "registers": int(m["launch__registers_per_thread"]),
+        "dram_write_GB": round(m["dram__bytes_write.sum"] / 1e9, 3), "dram_read_GB": round(m["dram__bytes_read.sum"] / 1e9, 4),
+        "threads_per_warp_inst": round(m["smsp__thread_inst_executed_per_inst_executed.ratio"], 1)})
+    if key:
+        counts[key] = round(fp64)
+json.dump(out, open(os.path.join(ROOT, "profiles", f"{tag}_configs_ncu.json"), "w"), indent=1)
+shutil.copy(src, os.path.join(ROOT, "profiles", f"{tag}_configs_metrics.csv"))
+path = os.path.join(ROOT, "profiles", "fp64_pipe.json")
+pipe = json.load(open(path))
+pipe["fp64_inst_per_event"] = counts
+pipe["what"] = pipe["what"].replace("r01_v5_configs_ncu.json", f"{tag}_configs_ncu.json")
+json.dump(pipe, open(path, "w"), indent=1)
+for k in out["kernels"]:
+    print(f"{k['config'][:44]:44s} {k['gpu_time_ms']:8.4f} ms  inst {k['warp_inst_per_warp_event']:7.1f}  fp64 {k['fp64_warp_inst_per_warp_event']:7.1f} "
+          f"({k['fp64_pipe_pct_of_peak']:.0f} % of pipe)  issue {k['issue_active_pct']:.0f} %  regs {k['registers']}")
