@@ -635,6 +635,10 @@ int fill_params(const ps_tree* t, PsParams& p, uint64_t seed, uint64_t first_eve
     if (t->n_user > 0 && !user_masses) return fail(PS_E_INVALID, "tree has %d user-mass particles but user_masses is NULL", t->n_user);
     p = t->base;
     p.seed = seed;
+    for (int r = 0; r < 10; ++r) {
+        p.philox_keys[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        p.philox_keys[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     p.first_event = first_event;
     p.n_events = n_events;
     p.event_index = (const long long*)event_index;

@@ -66,6 +66,9 @@ struct Pt {
     static constexpr bool sampled = (KIND == PS_KIND_GAUSS || KIND == PS_KIND_BW || KIND == PS_KIND_RELBW);
     static constexpr int n_below = (0 + ... + (1 + Ch::n_below));
     static constexpr int n_sampled_children = (0 + ... + (Ch::sampled ? 1 : 0));
+    // uniform draws of this node and of everything below it (ps_tree_n_draws): 3n-4 per decay + one per sampled child
+    static constexpr int n_draws =
+        (sizeof...(Ch) == 0 ? 0 : (int)(3 * sizeof...(Ch)) - 4 + n_sampled_children) + (0 + ... + Ch::n_draws);
     static constexpr bool resonant_leaf_below =
         (false || ... || ((Ch::nch == 0 && Ch::kind != PS_KIND_FIXED) || Ch::resonant_leaf_below));
     static constexpr bool has_grandchildren = (false || ... || (Ch::nch > 0));
@@ -114,12 +117,17 @@ struct WmaxAcc {
 // ------------------------------------------------------------------ per-event state
 // WONLY: only the event weight is wanted (the accept-reject mask pass): no kinematics, and the weight -- like the
 // maximum weight -- is accumulated as a product in wacc instead of being formed factor by factor.
-template <int P, bool DBG, bool WONLY = false>
+// KEYED: the Philox round keys are read from the parameter block (PsParams::philox_keys) instead of being re-derived from
+// the seed with twenty uniform-datapath additions per tile.  Measured: flat four-body decay 2.61 -> 2.54 ms per 1e8 events
+// (578 -> 545 instructions per loop iteration), but the memory-bound three-body decay 1.562 -> 1.577 ms (four more
+// registers, a different store schedule), so the small trees keep the seed form (use_keyed_philox).
+template <int P, bool DBG, bool WONLY = false, bool KEYED = true>
 struct Ctx {
     static constexpr bool wonly = WONLY && !PS_EXACT;
     double px[P], py[P], pz[P], en[P], ms[P];
     WmaxAcc wacc;  // 1 / (product of the two-body momenta of the event), wonly
     unsigned long long seed, event;
+    const unsigned int* keys;  // PsParams::philox_keys
     const double* dbg_row;
     unsigned int w[4];  // Philox block currently being consumed
     bool bad;
@@ -134,12 +142,12 @@ struct Ctx {
         constexpr int FB = bit0 / 128, LB = (bit0 + PS_UNIFORM_BITS - 1) / 128;
         constexpr int PREV = COL == 0 ? -1 : (bit0 - 1) / 128;  // last block touched by the previous column
         if constexpr (FB > PREV) {
-            const Philox4 r = philox4x32_10(seed, event, FB, 0u);
+            const Philox4 r = KEYED ? philox4x32_10_keyed(keys, event, FB, 0u) : philox4x32_10(seed, event, FB, 0u);
             w[0] = r.w[0], w[1] = r.w[1], w[2] = r.w[2], w[3] = r.w[3];
         }
         unsigned int x[8] = {w[0], w[1], w[2], w[3], 0u, 0u, 0u, 0u};
         if constexpr (LB > FB) {
-            const Philox4 r = philox4x32_10(seed, event, LB, 0u);
+            const Philox4 r = KEYED ? philox4x32_10_keyed(keys, event, LB, 0u) : philox4x32_10(seed, event, LB, 0u);
             x[4] = r.w[0], x[5] = r.w[1], x[6] = r.w[2], x[7] = r.w[3];
             w[0] = r.w[0], w[1] = r.w[1], w[2] = r.w[2], w[3] = r.w[3];
         }
@@ -730,6 +738,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 //       dispatches CTAs in index order, so chip-wide the stores sweep HBM in address order like a
 //       memset (tools/store_bench.cu: 7.3-7.5 TB/s against 6.3 TB/s for the persistent stride, whose
 //       CTAs drift apart); best for memory-bound trees (2 bodies).
+// trees with more than PS_KEYED_MIN_DRAWS uniform draws per event read precomputed Philox round keys (see Ctx)
+#ifndef PS_KEYED_MIN_DRAWS
+#define PS_KEYED_MIN_DRAWS 5
+#endif
+template <class Tree>
+__host__ __device__ constexpr bool use_keyed_philox() {
+    return Tree::n_draws > PS_KEYED_MIN_DRAWS;
+}
+
 template <class Tree, bool BOOST, bool DBG>
 __device__ __forceinline__ void genbod_body(const PsParams& prm) {
     constexpr int P = Tree::n_below;
@@ -753,8 +770,9 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
         {
         const long long i = tile * PS_BLOCK + threadIdx.x;
         if (i < n) {
-            Ctx<P, DBG> c;
+            Ctx<P, DBG, false, use_keyed_philox<Tree>()> c;
             c.seed = prm.seed;
+            c.keys = prm.philox_keys;
             c.event = prm.event_index ? (unsigned long long)prm.event_index[i] : prm.first_event + (unsigned long long)i;
             c.dbg_row = DBG ? prm.dbg_u + i * prm.dbg_ncols : nullptr;
             c.bad = false;
@@ -849,8 +867,9 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
         const long long i = tile * PS_BLOCK + threadIdx.x;
         bool accept = false;
         if (i < n) {
-            Ctx<P, false, true> c;
+            Ctx<P, false, true, use_keyed_philox<Tree>()> c;
             c.seed = prm.seed;
+            c.keys = prm.philox_keys;
             c.event = prm.first_event + (unsigned long long)i;
             c.dbg_row = nullptr;
             c.bad = false;
@@ -859,7 +878,8 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
             const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
             double w_max, inv_w_max;
             event_w_max<Tree, BOOST>(c, prm, bx, by, bz, be, false, w_max, inv_w_max);
-            const double u = philox_uniform0(prm.seed, c.event, 1u);
+            const double u = use_keyed_philox<Tree>() ? philox_uniform0_keyed(prm.philox_keys, c.event, 1u)
+                                                      : philox_uniform0(prm.seed, c.event, 1u);
 #if PS_EXACT
             accept = u * w_bound * w_max < w;
 #else
@@ -976,8 +996,9 @@ __device__ __forceinline__ void genbod_hist_body(const PsParams& prm, const PsHi
     for (long long tile = blockIdx.x; tile * PS_BLOCK < n; tile += gridDim.x) {
         const long long i = tile * PS_BLOCK + threadIdx.x;
         if (i < n) {
-            Ctx<P, false> c;
+            Ctx<P, false, false, use_keyed_philox<Tree>()> c;
             c.seed = prm.seed;
+            c.keys = prm.philox_keys;
             c.event = prm.first_event + (unsigned long long)i;
             c.dbg_row = nullptr;
             c.bad = false;

@@ -51,6 +51,7 @@ typedef struct PsParams {
     double inv_wmax_const; /* its reciprocal */
 
     unsigned long long seed;
+    unsigned int philox_keys[20];   /* round keys of Philox4x32-10 for this seed: (lo, hi) + r (0x9E3779B9, 0xBB67AE85) */
     unsigned long long first_event; /* global index of local event 0: the Philox counter */
     long long n_events;
 

@@ -56,6 +56,29 @@ __device__ __forceinline__ Philox4 philox4x32_10(unsigned long long seed, unsign
     return out;
 }
 
+// The same with the ten round keys precomputed (rk[2 r], rk[2 r + 1] = key words of round r: the host derives them from
+// the seed into the kernel parameter block, PsParams::philox_keys), so that the kernel reads them as constants instead of
+// re-deriving them with twenty uniform-datapath additions per tile.
+__device__ __forceinline__ Philox4 philox4x32_10_keyed(const unsigned int* rk, unsigned long long event, unsigned int block,
+                                                       unsigned int stream) {
+    unsigned int c0 = (unsigned int)event, c1 = (unsigned int)(event >> 32), c2 = block, c3 = stream;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ rk[2 * r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c3 = lo0;
+    }
+    Philox4 out;
+    out.w[0] = c0;
+    out.w[1] = c1;
+    out.w[2] = c2;
+    out.w[3] = c3;
+    return out;
+}
+
 // 51 random bits (lo: 32, hi: low 19 bits used) -> U[0,1) with resolution 2^-51: the field fills the low
 // 51 mantissa bits of a double d in [1, 1.5), and u = 2 d - 2 is exact.
 __device__ __forceinline__ double uniform_from_bits(unsigned int lo, unsigned int hi) {
@@ -94,6 +117,11 @@ __device__ __forceinline__ double philox_uniform_col(unsigned long long seed, un
 // first uniform of block 0 of a stream (acceptance draws, stand-alone samplers)
 __device__ __forceinline__ double philox_uniform0(unsigned long long seed, unsigned long long event, unsigned int stream) {
     const Philox4 r = philox4x32_10(seed, event, 0u, stream);
+    return uniform_from_bits(r.w[0], r.w[1]);
+}
+
+__device__ __forceinline__ double philox_uniform0_keyed(const unsigned int* rk, unsigned long long event, unsigned int stream) {
+    const Philox4 r = philox4x32_10_keyed(rk, event, 0u, stream);
     return uniform_from_bits(r.w[0], r.w[1]);
 }
 
