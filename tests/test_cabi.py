@@ -74,6 +74,67 @@ def test_tree_compiler_matches_oracle(desc):
     lib.ps_tree_destroy(h)
 
 
+def _random_desc(rng, depth, counter, top=False, may_sample=False):
+    """A random decay tree: 2-4 children per decay, decaying intermediates fixed or sampled (at most one sampled child per
+    decay: with several, the reference's max_mass bookkeeping can produce forbidden events, phasespace.py:342-353), fixed
+    leaves."""
+    name = f"n{counter[0]}"
+    counter[0] += 1
+    decays = top or (depth > 0 and rng.random() < 0.5)
+    if not decays:
+        return (name, float(rng.uniform(0.0, 150.0)), "fixed", 0.0, [])
+    n_children = int(rng.integers(2, 5))
+    sampled_child = int(rng.integers(0, n_children))
+    children = [_random_desc(rng, depth - 1, counter, may_sample=(j == sampled_child)) for j in range(n_children)]
+    kind = str(rng.choice(["fixed", "gauss", "bw", "relbw"])) if may_sample else "fixed"
+    floor = sum(c[1] if c[2] == "fixed" else orc.recurse_stable(D.to_oracle(c)) for c in children)
+    mass = floor + float(rng.uniform(200.0, 900.0))  # always kinematically allowed at the pole masses
+    return (name, mass, kind, 0.0 if kind == "fixed" else float(rng.uniform(1.0, 80.0)), children)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_tree_compiler_matches_oracle_on_random_trees(seed):
+    """Slots (the reference's dict order), draw counts and recurse_stable() minimum masses of random trees with up to
+    four levels, 2-4 children per decay and all sampler kinds, and the analytic maximum weight."""
+    rng = np.random.default_rng(1000 + seed)
+    desc = _random_desc(rng, 3, [0], top=True)
+    rc, h, names = _tree(desc)
+    if rc != 0:  # more particles than PS_MAX_SLOTS: the only legitimate refusal of a well-formed tree
+        assert "more than" in _lib.last_error()
+        return
+    lib = _lib.lib
+    tree = D.to_oracle(desc)
+    order = orc.output_names(tree)
+    assert lib.ps_tree_n_particles(h) == len(order)
+    assert lib.ps_tree_n_draws(h) == orc.n_draws(tree)
+    slots = {names[i]: lib.ps_tree_slot(h, i) for i in range(len(names))}
+    assert slots.pop(names[0]) == -1
+    assert sorted(slots, key=slots.get) == order
+
+    def walk(d, part):
+        yield d, part
+        for dc, pc in zip(d[4], part.children):
+            yield from walk(dc, pc)
+
+    index = {n: i for i, n in enumerate(names)}
+    for d, part in walk(desc, tree):
+        if d[4] and d is not desc:
+            assert lib.ps_tree_min_mass(h, index[d[0]]) == pytest.approx(orc.recurse_stable(part), rel=1e-15)
+    # fixed leaves: the maximum weight depends on leaf masses only (recurse_w_max, phasespace.py:571-625), whatever the
+    # intermediate resonances were sampled at -- the host constant must equal the oracle's per-event value
+    n = 3
+    try:
+        _, ref_wmax, _ = orc.generate(tree, n, uniform_table(seed, 0, n, orc.n_draws(tree)), normalize_weights=False)
+    except FloatingPointError:
+        # several resonant siblings: the reference's max_mass ignores the minimum masses of the later ones
+        # (phasespace.py:342-353) and the events can come out forbidden -- nothing to compare the constant with
+        assert np.isfinite(lib.ps_tree_w_max(h))
+    else:
+        assert np.all(ref_wmax == ref_wmax[0])
+        np.testing.assert_allclose(lib.ps_tree_w_max(h), ref_wmax[0], rtol=1e-13)
+    lib.ps_tree_destroy(h)
+
+
 def test_min_mass_is_recurse_stable():
     rc, h, names = _tree(D.k1_gamma_desc())
     assert rc == 0
