@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PS_ABI_VERSION 2
+#define PS_ABI_VERSION 3
 
 /* mass model of a particle (GenParticle(name, mass): phasespace.py:100-119) */
 #define PS_MASS_FIXED 0 /* float mass: has_fixed_mass (phasespace.py:186-189) */
@@ -116,6 +116,9 @@ int ps_generate_host(const ps_tree* tree, uint64_t seed, uint64_t first_event, i
  *                      formed or stored), draws one extra uniform per event (Philox stream 1) and sets
  *                      bit (i%32) of mask[i/32] when u * w_bound < w / w_max; mask holds (n_events+31)/32
  *                      words and every one of them is written (bits past n_events are 0).
+ *                      overflow (device uint64, caller-zeroed, may be NULL) is incremented once per candidate
+ *                      with w / w_max > w_bound: those are accepted with probability 1 instead of > 1, so a
+ *                      non-zero count means w_bound was too small and the accepted sample is biased.
  *   ps_unweight_scan   exclusive prefix sum of the accepted events per tile of 256 events (the population
  *                      counts of the tile's eight mask words): tile_offsets[t] (device, (n_events+255)/256
  *                      entries) = accepted events before tile t, *total (device) = all accepted events.
@@ -123,7 +126,7 @@ int ps_generate_host(const ps_tree* tree, uint64_t seed, uint64_t first_event, i
  *   ps_unweight_index  turns mask + tile_offsets into the sorted list of accepted global event indices
  *                      (feed to ps_generate_indexed). */
 int ps_unweight_mask(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events, double w_bound,
-                     uint32_t* mask, int32_t* err_flag, uint32_t flags, void* stream);
+                     uint32_t* mask, uint64_t* overflow, int32_t* err_flag, uint32_t flags, void* stream);
 int ps_unweight_scan(const uint32_t* mask, int64_t n_events, int64_t* tile_offsets, int64_t* total, void* stream);
 int ps_unweight_index(const uint32_t* mask, const int64_t* tile_offsets, uint64_t first_event, int64_t n_events,
                       int64_t* event_index, void* stream);

@@ -16,7 +16,7 @@ PS_MASS_FIXED, PS_MASS_GAUSS, PS_MASS_BW, PS_MASS_RELBW, PS_MASS_USER = range(5)
 PS_GEN_NORMALIZE, PS_GEN_EXACT = 1, 2
 PS_E_INVALID, PS_E_CUDA, PS_E_COMPILE, PS_E_FORBIDDEN = -1, -2, -3, -4
 TILE = 256  # events per tile of the unweighting mask kernel
-ABI_VERSION = 2  # PS_ABI_VERSION of include/phasespace_b200.h this binding was written against
+ABI_VERSION = 3  # PS_ABI_VERSION of include/phasespace_b200.h this binding was written against
 
 
 class NodeDesc(ctypes.Structure):
@@ -52,7 +52,7 @@ def _load():
         "ps_generate": (c.c_int, [vp, u64, u64, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, u32, vp]),
         "ps_generate_indexed": (c.c_int, [vp, u64, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, u32, vp]),
         "ps_generate_host": (c.c_int, [vp, u64, u64, i64, vp, i64, vp, vp, vp, i64, u32]),
-        "ps_unweight_mask": (c.c_int, [vp, u64, u64, i64, dbl, vp, vp, u32, vp]),
+        "ps_unweight_mask": (c.c_int, [vp, u64, u64, i64, dbl, vp, vp, vp, u32, vp]),
         "ps_unweight_scan": (c.c_int, [vp, i64, vp, vp, vp]),
         "ps_unweight_index": (c.c_int, [vp, vp, u64, i64, vp, vp]),
         "ps_histogram": (c.c_int, [vp, u64, u64, i64, vp, i64, i32, dbl, dbl, dbl, dbl, dbl, vp, vp, u32, vp]),

@@ -519,8 +519,8 @@ int jit_compile(const KernelKey& key, const void** fn_out) {
         src += "extern \"C\" __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) ps_jit_kernel(const __grid_constant__ PsParams prm, const __grid_constant__ psk::PsHistParams h) {\n"
                "  psk::genbod_hist_body<" + key.sig + ", " + (key.boost ? "true" : "false") + ">(prm, h);\n}\n";
     } else {
-        src += "extern \"C\" __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) ps_jit_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask) {\n"
-               "  psk::genbod_mask_body<" + key.sig + ", " + (key.boost ? "true" : "false") + ">(prm, w_bound, mask);\n}\n";
+        src += "extern \"C\" __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) ps_jit_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask, unsigned long long* overflow) {\n"
+               "  psk::genbod_mask_body<" + key.sig + ", " + (key.boost ? "true" : "false") + ">(prm, w_bound, mask, overflow);\n}\n";
     }
     std::vector<const char*> hdr_text, hdr_name;
     for (const EmbeddedHeader* h = kEmbeddedHeaders; h->name; ++h) {
@@ -952,7 +952,7 @@ __global__ void __launch_bounds__(PS_BLOCK) index_kernel(const unsigned int* mas
 }  // namespace
 
 extern "C" int ps_unweight_mask(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events, double w_bound,
-                                uint32_t* mask, int32_t* err_flag, uint32_t flags, void* stream) {
+                                uint32_t* mask, uint64_t* overflow, int32_t* err_flag, uint32_t flags, void* stream) {
     if (!tree || !mask) return fail(PS_E_INVALID, "null argument");
     if (tree->n_user > 0) return fail(PS_E_INVALID, "unweighting does not take user-mass trees");
     if (!(w_bound > 0.0)) return fail(PS_E_INVALID, "w_bound must be > 0");
@@ -969,7 +969,7 @@ extern "C" int ps_unweight_mask(const ps_tree* tree, uint64_t seed, uint64_t fir
     PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
     int grid = (int)((long long)sms * 8 < tiles ? (long long)sms * 8 : tiles);
-    void* args[] = {&p, &w_bound, &mask};
+    void* args[] = {&p, &w_bound, &mask, &overflow};
     PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, 0, (cudaStream_t)stream));
     g_launches.fetch_add(1);
     return 0;

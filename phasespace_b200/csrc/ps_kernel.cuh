@@ -856,8 +856,12 @@ __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) genbod_kernel(const _
 // accept = (u * w_bound < w / w_max) as one bit per event.  Together with
 // ps_unweight_scan / ps_unweight_index this yields the accepted events ordered by event index,
 // independent of grid size or GPU count; ps_generate_indexed then regenerates only those.
+// overflow (optional): number of candidates whose normalised weight exceeds w_bound -- such an event is accepted with
+// probability 1 instead of w / w_bound > 1, i.e. the bound was too small and the sample is biased by exactly those
+// events.  One compare and one ballot per event; the atomic only fires for warps that saw one.
 template <class Tree, bool BOOST>
-__device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_bound, unsigned int* mask) {
+__device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_bound, unsigned int* mask,
+                                                 unsigned long long* overflow) {
     constexpr int P = Tree::n_below;
     const long long n = prm.n_events;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -865,7 +869,7 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
     // no CTA-wide synchronisation: the per-tile counts the scan needs are the population counts of the mask words
     for (long long tile = blockIdx.x; tile * PS_BLOCK < n; tile += gridDim.x) {
         const long long i = tile * PS_BLOCK + threadIdx.x;
-        bool accept = false;
+        bool accept = false, over = false;
         if (i < n) {
             Ctx<P, false, true, use_keyed_philox<Tree>()> c;
             c.seed = prm.seed;
@@ -882,25 +886,31 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
                                                       : philox_uniform0(prm.seed, c.event, 1u);
 #if PS_EXACT
             accept = u * w_bound * w_max < w;
+            over = w_bound * w_max < w;
 #else
             // w = 1 / c.wacc.inverse(): u w_bound < w / w_max  <=>  u w_bound / w < 1 / w_max  (w = 0: inf, rejected)
-            accept = u * w_bound * c.wacc.inverse() < inv_w_max;
+            const double bound_over_w = w_bound * c.wacc.inverse();
+            accept = u * bound_over_w < inv_w_max;
+            over = bound_over_w < inv_w_max;
             (void)w;
 #endif
             bad_any |= c.bad;
         }
         const unsigned int word = __ballot_sync(0xffffffffu, accept);
+        const unsigned int over_word = __ballot_sync(0xffffffffu, over);
         const long long wi = tile * (PS_BLOCK / 32) + wid;
         if (lane == 0 && wi * 32 < n) mask[wi] = word;
+        if (lane == 0 && over_word && overflow) atomicAdd(overflow, (unsigned long long)__popc(over_word));
     }
     if (bad_any) *prm.err_flag = PS_ERR_FORBIDDEN;
 }
 
 template <class Tree, bool BOOST, int EXACT>
 __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS)
-    genbod_mask_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask) {
+    genbod_mask_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask,
+                       unsigned long long* overflow) {
     static_assert(EXACT == PS_EXACT, "variant tag must match the translation unit");
-    genbod_mask_body<Tree, BOOST>(prm, w_bound, mask);
+    genbod_mask_body<Tree, BOOST>(prm, w_bound, mask, overflow);
 }
 
 // ------------------------------------------------------------------ fused weighted histograms

@@ -52,6 +52,31 @@ except AttributeError:  # pragma: no cover
         return torch.cuda.current_stream(index).cuda_stream
 
 
+def _check_out(t, name, shape, device, dtype=torch.float64, pinned_host=False):
+    """A caller-supplied output buffer goes to the C ABI as a bare pointer: anything but the exact shape, dtype,
+    device and a dense layout would make the kernel (or the D2H copies) write out of bounds."""
+    if t is None:
+        return
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"out[{name!r}] must be a torch tensor, not {type(t).__name__}")
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"out[{name!r}] must have shape {tuple(shape)}, not {tuple(t.shape)}")
+    if t.dtype != dtype:
+        raise ValueError(f"out[{name!r}] must have dtype {dtype}, not {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"out[{name!r}] must be contiguous")
+    if pinned_host:
+        if t.device.type != "cpu":
+            raise ValueError(f"out[{name!r}] must be a CPU tensor, not on {t.device}")
+    elif t.device != device:
+        raise ValueError(f"out[{name!r}] must be on {device}, not on {t.device}")
+
+
+def _structure(part):
+    """Identity of a decay tree: which GenParticle objects hang where (masses cannot change after construction)."""
+    return (id(part), tuple(_structure(c) for c in part.children))
+
+
 def process_list_to_tensor(lst, device=None):
     """ps.py:37-53 -- a Python *list* is transposed (read as ``(4, N)``), anything else is taken as is."""
     if isinstance(lst, list):
@@ -82,7 +107,11 @@ class CompiledDecay:
             idx = len(self.particles)
             self.particles.append(part)
             kind, mass, width = _lib.PS_MASS_FIXED, 0.0, 0.0
-            if part.has_fixed_mass:
+            if parent == -1 and not part.has_fixed_mass:
+                # ps.py:534-543: a resonance may be the generating particle when boost_to is given -- its mass is then
+                # kin.mass(boost_to), evaluated per event by the BOOST kernel, and the mass function is never called
+                mass = float("nan")
+            elif part.has_fixed_mass:
                 mass = float(np.asarray(part._mass_val, dtype=np.float64).reshape(-1)[0])
             elif split:
                 kind = _lib.PS_MASS_USER
@@ -107,6 +136,8 @@ class CompiledDecay:
         self.names = sorted(self.slots, key=self.slots.get)
         self.user_columns = {i: lib.ps_tree_user_column(handle, i) for i in range(len(descs))}
         self.has_resonances = any(d[1] != _lib.PS_MASS_FIXED for d in descs)
+        self.top_is_resonance = not top.has_fixed_mass
+        self.structure = _structure(top)
         self._err_flags = {}
         self._static_forbidden = self._check_static()
 
@@ -177,9 +208,16 @@ class CompiledDecay:
         """
         device = _device()
         n = int(n_events)
+        if self.top_is_resonance and boost_to is None:
+            raise ValueError("Cannot use resonance as top particle")  # ps.py:543
         out = out or {}
         weights, particles = out.get("weights"), out.get("particles")
         weights_max = out.get("weights_max") if not normalize_weights else None
+        _check_out(weights, "weights", (n,), device)
+        _check_out(particles, "particles", (self.n_particles, n, 4), device)
+        _check_out(weights_max, "weights_max", (n,), device)
+        _check_out(stats, "stats", (4,), device)
+        _check_out(err, "err", (1,), device, dtype=torch.int32)
         if weights is None and particles is None and weights_max is None:
             # one allocation for everything: [particles (P,n,4) | weights (n) | weights_max (n)]
             extra = 1 if normalize_weights else 2
@@ -325,7 +363,8 @@ class GenParticle:
 
     def compile(self) -> CompiledDecay:
         """Compile (once) the decay tree below this particle into its kernel descriptor."""
-        if self._compiled is None:
+        # a leaf can still get children after this tree was compiled (ps.py:207-210 latches decaying particles only)
+        if self._compiled is None or self._compiled.structure != _structure(self):
             def fused(part):
                 return all(
                     (c.has_fixed_mass or hasattr(c._mass, "_ps_sampler")) and fused(c) for c in part.children
@@ -461,6 +500,7 @@ class GenParticle:
             t = out.get(key)
             if t is None:
                 t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+            _check_out(t, key, shape, None, pinned_host=True)
             return t
 
         weights = pinned("weights", (n_events,))

@@ -12,6 +12,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from ._lib import ForbiddenDecayError
+
 
 def shard_range(n_events: int, rank: int, world: int) -> tuple[int, int]:
     """``(first, count)`` of rank ``rank``: ranges of ``ceil(n/world)`` events, the last ones shorter."""
@@ -29,12 +31,17 @@ def _rank_world(group=None):
 
 
 def generate_sharded(decay, n_events: int, seed: int, *, boost_to=None, normalize_weights=True, group=None,
-                     stats=None, first_event: int = 0, exact: bool = False):
+                     stats=None, first_event: int = 0, exact: bool = False, err=None):
     """This rank's share of ``decay.generate(n_events, seed=seed)``.
 
     Returns ``(first, count, weights, weights_max | None, particles)`` with ``particles`` a dict of
     ``(count, 4)`` CUDA tensors.  ``boost_to`` (if per event) is the *full* ``(n_events, 4)`` array or this
     rank's rows.  Outputs stay on their GPUs; gather them only if a consumer really needs one tensor.
+
+    A kinematically forbidden decay raises ``ForbiddenDecayError`` exactly as ``generate`` does (the reference asserts
+    "Forbidden decay", ps.py:357-363): statically for all-fixed masses, otherwise from the kernel's error flag, which
+    costs one 4-byte read-back -- unless the caller passes its own zeroed ``err`` tensor ``(1,)`` int32 and checks
+    it later (several launches can share one flag and one synchronisation).
     """
     rank, world = _rank_world(group)
     first, count = shard_range(n_events, rank, world)
@@ -42,6 +49,8 @@ def generate_sharded(decay, n_events: int, seed: int, *, boost_to=None, normaliz
     if compiled.n_user:
         raise ValueError("sharded generation needs in-kernel mass functions (no arbitrary Python callables)")
     decay._mark_generate_called()
+    if compiled._static_forbidden is not None and boost_to is None:
+        raise ForbiddenDecayError(f"Forbidden decay (particle {compiled._static_forbidden})")
     if boost_to is not None:
         boost_to = torch.as_tensor(boost_to, dtype=torch.float64).reshape(-1, 4)
         if boost_to.shape[0] == n_events and n_events != 1:
@@ -50,9 +59,12 @@ def generate_sharded(decay, n_events: int, seed: int, *, boost_to=None, normaliz
             raise ValueError(f"The number of events requested ({n_events}) doesn't match the boost_to input size "
                              f"of {tuple(boost_to.shape)}")
         boost_to = boost_to.to(torch.device("cuda", torch.cuda.current_device())).contiguous()
+    deferred = err is not None
     weights, weights_max, slab, err = compiled.launch(
         count, seed, first_event + first, boost_to=boost_to, normalize_weights=normalize_weights, exact=exact,
-        stats=stats)
+        stats=stats, err=err)
+    if not deferred and count > 0 and (compiled.has_resonances or boost_to is not None) and int(err.item()):
+        raise ForbiddenDecayError("Forbidden decay")
     parts = {name: slab[compiled.slots[name]] for name in compiled.names}
     return first, count, weights, weights_max, parts
 

@@ -24,15 +24,26 @@ from .phasespace import _device, _ptr
 _CAPACITY_STEP = 1 << 16  # events
 
 
+class UnweightingOverflowError(RuntimeError):
+    """``w / w_max`` exceeded ``w_bound`` for some candidates: the accepted sample would be biased."""
+
+
 def generate_unweighted(decay, n_events: int, seed: int, *, w_bound: float = 1.0, first_event: int = 0,
-                        exact: bool = False):
+                        exact: bool = False, return_overflow: bool = False, on_overflow: str = "raise"):
     """Unweighted events among the candidates ``[first_event, first_event + n_events)`` of stream ``seed``.
 
     ``w_bound`` is the acceptance bound on the *normalised* weight ``w / w_max`` (1.0 is always safe; a
     smaller measured maximum raises the efficiency).  Returns ``(particles, event_index, weights)``:
     ``particles`` maps names to ``(n_accepted, 4)`` tensors, ``event_index`` the accepted global event
     indices (int64, ascending) and ``weights`` their normalised weights.
+
+    A candidate with ``w / w_max > w_bound`` would have to be accepted with probability above one, so a bound that
+    is too small biases the sample.  The mask pass counts those candidates; ``on_overflow`` says what a non-zero
+    count does: ``"raise"`` (default) raises :class:`UnweightingOverflowError`, ``"warn"`` warns, ``"ignore"``
+    nothing.  With ``return_overflow=True`` the count is returned as a fourth value (and never raises).
     """
+    if on_overflow not in ("raise", "warn", "ignore"):
+        raise ValueError("on_overflow must be 'raise', 'warn' or 'ignore'")
     device = _device()
     n = int(n_events)
     compiled = decay.compile()
@@ -44,18 +55,26 @@ def generate_unweighted(decay, n_events: int, seed: int, *, w_bound: float = 1.0
     n_tiles = (n + _lib.TILE - 1) // _lib.TILE
     mask = torch.empty(((n + 31) // 32,), dtype=torch.int32, device=device)
     offsets = torch.empty((max(n_tiles, 1),), dtype=torch.int64, device=device)
-    # [accepted count (int64) | error flag (int32, low half of the second word)]: one read-back for both
-    state = torch.zeros((2,), dtype=torch.int64, device=device)
-    total, err = state[:1], state[1:].view(torch.int32)[:1]
+    # [accepted count (int64) | error flag (int32, low half of the word) | overflow count]: one read-back for all
+    state = torch.zeros((3,), dtype=torch.int64, device=device)
+    total, err, over = state[:1], state[1:2].view(torch.int32)[:1], state[2:]
     flags = _lib.PS_GEN_EXACT if exact else 0
     seed = int(seed) & (2**64 - 1)
     if n > 0:
         _lib.check(lib.ps_unweight_mask(compiled.handle, seed, int(first_event), n, float(w_bound), _ptr(mask),
-                                        _ptr(err), flags, stream))
+                                        _ptr(over), _ptr(err), flags, stream))
         _lib.check(lib.ps_unweight_scan(_ptr(mask), n, _ptr(offsets), _ptr(total), stream))
-    n_acc, failed = state.tolist()
+    n_acc, failed, n_over = state.tolist()
     if failed:
         raise _lib.ForbiddenDecayError("Forbidden decay")
+    if n_over and not return_overflow and on_overflow != "ignore":
+        msg = (f"{n_over} of {n} candidates have w / w_max > w_bound = {w_bound!r}: the bound is too small and "
+               "the accepted sample would be biased; raise w_bound (1.0 is always safe)")
+        if on_overflow == "raise":
+            raise UnweightingOverflowError(msg)
+        import warnings
+
+        warnings.warn(msg, RuntimeWarning, stacklevel=2)
     # Capacity rounded up to a multiple of 65536 events: consecutive chunks of a long run accept slightly different
     # numbers of events, and buffers of a size seen before come out of torch's caching allocator instead of cudaMalloc
     # (which costs more than a millisecond for the 3 GB slab of a 10-body chunk).
@@ -70,4 +89,6 @@ def generate_unweighted(decay, n_events: int, seed: int, *, w_bound: float = 1.0
             int(4 * max(cap, 1)), None, _ptr(err), flags | _lib.PS_GEN_NORMALIZE, stream))
     slab = slab[:, :n_acc]
     parts = {name: slab[compiled.slots[name]] for name in compiled.names}
+    if return_overflow:
+        return parts, index, weights, int(n_over)
     return parts, index, weights

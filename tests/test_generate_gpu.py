@@ -43,11 +43,55 @@ def test_n_events(n_events):
     assert len(w2) == n_events
 
 
-def test_as_vectors():
-    pytest.importorskip("vector")
+@pytest.fixture
+def vector_module(monkeypatch):
+    """The real ``vector`` package when it is installed, else the test stand-in (tests/helpers/vector_standin.py),
+    so that the product's conversion code (ps.py:676-695, 817-835) always runs."""
+    try:
+        import vector
+    except ImportError:
+        import sys
+
+        from .helpers import vector_standin as vector
+
+        monkeypatch.setitem(sys.modules, "vector", vector)
+    return vector
+
+
+@pytest.mark.parametrize("n_events", [1, 5, 523])
+def test_as_vectors(vector_module, n_events):
+    """tests/test_generate.py:34-63 of the reference, as_vectors=True."""
     decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
-    _, particles = decay.generate(n_events=5, as_vectors=True)
-    assert all(np.stack([p.px, p.py, p.pz, p.E], axis=-1).shape == (5, 4) for p in particles.values())
+    w, particles = decay.generate(n_events=n_events, as_vectors=True, seed=4)
+    assert all(isinstance(p, vector_module.Momentum) and isinstance(p, vector_module.Lorentz) for p in particles.values())
+    stacked = {k: np.stack([p.px, p.py, p.pz, p.E], axis=-1) for k, p in particles.items()}
+    assert len(stacked) == 3 and all(v.shape == (n_events, 4) for v in stacked.values())
+    _, tensors = decay.generate(n_events=n_events, seed=4)
+    assert all(np.array_equal(stacked[k], _np(tensors[k])) for k in tensors)
+    again = phasespace.to_vectors(tensors)
+    assert all(np.array_equal(again[k].energy, stacked[k][:, 3]) for k in tensors)
+
+
+def test_boost_to_as_vector_object(vector_module):
+    """ps.py:676-695 (tests/test_physics.py:192-199 of the reference): a ``vector`` momentum Lorentz array as boost_to
+    gives the same events as the equivalent (n, 4) array; anything else that is a ``vector`` object is refused."""
+    n = 257
+    rng = np.random.default_rng(8)
+    p = rng.normal(0.0, 20000.0, (n, 3))
+    e = np.sqrt((p * p).sum(1) + B0_MASS**2)
+    booster = vector_module.array(dict(px=p[:, 0], py=p[:, 1], pz=p[:, 2], e=e))  # the spelling of tests/test_physics.py:193-199
+    decay = D.to_gen(D.kstar_gamma_desc("relbw"))
+    w_v, parts_v = decay.generate(n, boost_to=booster, seed=6)
+    w_a, parts_a = decay.generate(n, boost_to=np.concatenate([p, e[:, None]], axis=1), seed=6)
+    assert torch.equal(w_v, w_a) and all(torch.equal(parts_v[k], parts_a[k]) for k in parts_a)
+    total = _np(parts_v["K*0"] + parts_v["gamma"])
+    assert np.max(np.abs(total - np.concatenate([p, e[:, None]], axis=1))) / e.max() < 1e-12
+    with pytest.raises(ValueError, match="momentum Lorentz vector"):
+        decay.generate(n, boost_to=vector_module.array({"x": p[:, 0], "y": p[:, 1], "z": p[:, 2], "t": e}))
+    with pytest.raises(ValueError, match="momentum Lorentz vector"):
+        decay.generate(n, boost_to=vector_module.array({"px": p[:, 0], "py": p[:, 1], "pz": p[:, 2]}))
+    with pytest.raises(ValueError, match="doesn't match the boost_to input size"):
+        decay.generate(n + 1, boost_to=booster)
 
 
 def test_deterministic_events():
@@ -467,3 +511,121 @@ def test_covering_grid_with_several_tiles_per_cta(which):
         wp, _, sp, _ = comp.launch(count, seed, first_event=first)
         assert torch.equal(wp, w[first:first + count])
         assert torch.equal(sp, slab[:, first:first + count])
+
+
+def test_out_buffers_are_validated():
+    """Caller-supplied output buffers reach the C ABI as bare pointers: wrong shape, dtype, device or layout must be
+    refused on the host instead of letting the kernel (or the D2H copies) write out of bounds."""
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    comp = decay.compile()
+    n, dev = 1000, torch.device("cuda", torch.cuda.current_device())
+    good = {"weights": torch.empty((n,), dtype=torch.float64, device=dev),
+            "particles": torch.empty((3, n, 4), dtype=torch.float64, device=dev)}
+    comp.launch(n, seed=1, out=good)
+    bad = [
+        ("weights", torch.empty((n - 1,), dtype=torch.float64, device=dev)),                 # too small
+        ("weights", torch.empty((n,), dtype=torch.float32, device=dev)),                     # dtype
+        ("weights", torch.empty((2 * n,), dtype=torch.float64, device=dev)[::2]),            # strided
+        ("weights", torch.empty((n,), dtype=torch.float64)),                                 # host memory
+        ("particles", torch.empty((3, n - 1, 4), dtype=torch.float64, device=dev)),          # too small
+        ("particles", torch.empty((2, n, 4), dtype=torch.float64, device=dev)),              # a plane short
+        ("particles", torch.empty((3, 4, n), dtype=torch.float64, device=dev).permute(0, 2, 1)),  # layout
+        ("particles", np.empty((3, n, 4))),                                                  # not a tensor
+    ]
+    for key, tensor in bad:
+        with pytest.raises(ValueError, match=key):
+            comp.launch(n, seed=1, out={**good, key: tensor})
+    with pytest.raises(ValueError, match="weights_max"):
+        comp.launch(n, seed=1, normalize_weights=False, out={**good, "weights_max": torch.empty((5,), dtype=torch.float64, device=dev)})
+    with pytest.raises(ValueError, match="stats"):
+        comp.launch(n, seed=1, out=good, stats=torch.zeros((3,), dtype=torch.float64, device=dev))
+    with pytest.raises(ValueError, match="err"):
+        comp.launch(n, seed=1, out=good, err=torch.zeros((1,), dtype=torch.int64, device=dev))
+    # host delivery: pinned or not, the buffers must be CPU tensors of the exact shape
+    host_good = {"weights": torch.empty((n,), dtype=torch.float64, pin_memory=True),
+                 "particles": torch.empty((3, n, 4), dtype=torch.float64, pin_memory=True)}
+    decay.generate_host(n, seed=1, out=host_good)
+    with pytest.raises(ValueError, match="particles"):
+        decay.generate_host(n, seed=1, out={**host_good, "particles": torch.empty((3, n // 2, 4), dtype=torch.float64)})
+    with pytest.raises(ValueError, match="weights"):
+        decay.generate_host(n, seed=1, out={**host_good, "weights": good["weights"]})  # a CUDA tensor
+
+
+def test_sharded_generation_reports_forbidden_decays():
+    """generate_sharded raises where generate() would (the reference asserts "Forbidden decay", ps.py:357-363)."""
+    from phasespace_b200 import sharding
+
+    with pytest.raises(phasespace.ForbiddenDecayError):  # statically forbidden masses
+        sharding.generate_sharded(phasespace.nbody_decay(300.0, [PION_MASS] * 3), 100, seed=1)
+    boost = np.array([[0.0, 0.0, 100.0, 250.0]])  # invariant mass too small for three pions
+    with pytest.raises(phasespace.ForbiddenDecayError):
+        sharding.generate_sharded(phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3), 100, seed=1, boost_to=boost)
+    # a resonance squeezed out by its sibling: K* (min 633) next to a 4700 MeV particle in a 5279 MeV parent
+    from phasespace_b200.fromdecay import mass_functions as mf
+
+    squeezed = GenParticle("B", B0_MASS).set_children(
+        GenParticle("K*", mf.gauss_factory(895.81, 47.4)).set_children(GenParticle("K", D.KAON_MASS), GenParticle("pi", PION_MASS)),
+        GenParticle("X", 4700.0))
+    with pytest.raises(phasespace.ForbiddenDecayError):
+        squeezed.generate(100, seed=1)
+    squeezed2 = GenParticle("B", B0_MASS).set_children(
+        GenParticle("K*", mf.gauss_factory(895.81, 47.4)).set_children(GenParticle("K", D.KAON_MASS), GenParticle("pi", PION_MASS)),
+        GenParticle("X", 4700.0))
+    with pytest.raises(phasespace.ForbiddenDecayError):
+        sharding.generate_sharded(squeezed2, 100, seed=1)
+    # deferred check: the caller's flag is set, nothing raises
+    err = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    sharding.generate_sharded(phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3), 100, seed=1, boost_to=boost, err=err)
+    assert int(err.item()) == 1
+    # and an allowed decay still comes back, identical to generate()
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    first, count, w, w_max, parts = sharding.generate_sharded(decay, 1000, seed=4)
+    w_ref, p_ref = decay.generate(1000, seed=4)
+    assert (first, count) == (0, 1000) and torch.equal(w, w_ref) and torch.equal(parts["p_1"], p_ref["p_1"])
+
+
+def test_resonance_as_generating_particle_with_boost_to():
+    """ps.py:534-543: a resonance may be the particle generate() is called on when boost_to is given -- its mass is then
+    kin.mass(boost_to) and the mass function is never called (what the recursion does for every decaying child)."""
+    from phasespace_b200.fromdecay import mass_functions as mf
+
+    kstar = GenParticle("K*0", mf.relativistic_breitwigner_factory(D.KSTARZ_MASS, D.KSTARZ_WIDTH)).set_children(
+        GenParticle("K+", D.KAON_MASS), GenParticle("pi-", PION_MASS))
+    with pytest.raises(ValueError, match="Cannot use resonance as top particle"):
+        kstar.generate(10)
+    n = 5000
+    m = np.random.default_rng(3).uniform(700.0, 1100.0, n)
+    p = np.random.default_rng(4).normal(0.0, 2000.0, (n, 3))
+    boost = np.concatenate([p, np.sqrt((p * p).sum(1) + m * m)[:, None]], axis=1)
+    w, parts = kstar.generate(n, boost_to=boost, seed=2)
+    assert list(parts) == ["K+", "pi-"]
+    total = _np(parts["K+"] + parts["pi-"])
+    assert np.max(np.abs(total - boost)) / np.max(boost[:, 3]) < 1e-12
+    # the same events as a fixed-mass particle of any mass boosted to the same rows (the top mass comes from boost_to)
+    fixed = GenParticle("K*0", 900.0).set_children(GenParticle("K+", D.KAON_MASS), GenParticle("pi-", PION_MASS))
+    w2, parts2 = fixed.generate(n, boost_to=boost, seed=2)
+    assert torch.equal(w, w2) and torch.equal(parts["K+"], parts2["K+"])
+    # a Python callable as mass function of the generating particle is never evaluated either
+    def never(min_mass, max_mass, n_events):
+        raise AssertionError("the generating particle's mass function must not be called")
+
+    top = GenParticle("R", never).set_children(GenParticle("a", D.KAON_MASS), GenParticle("b", PION_MASS))
+    w3, parts3 = top.generate(n, boost_to=boost, seed=2)
+    assert torch.equal(w3, w) and torch.equal(parts3["a"], parts["K+"])
+    with pytest.raises(ValueError, match="Cannot use resonance as top particle"):
+        top.compile().launch(10, seed=1)
+
+
+def test_children_added_to_a_leaf_after_compilation():
+    """The reference latches only decaying particles (ps.py:207-210, 318): a leaf can still get children after its
+    parent has generated, and later generate() calls must include them (no stale compiled tree)."""
+    kstar = GenParticle("K*0", D.KSTARZ_MASS)
+    top = GenParticle("B0", B0_MASS).set_children(kstar, GenParticle("gamma", 0.0))
+    w, parts = top.generate(100, seed=1)
+    assert list(parts) == ["K*0", "gamma"]
+    kstar.set_children(GenParticle("K+", D.KAON_MASS), GenParticle("pi-", PION_MASS))
+    w, parts = top.generate(100, seed=1)
+    assert list(parts) == ["K*0", "gamma", "K+", "pi-"]
+    assert float((parts["K+"] + parts["pi-"] - parts["K*0"]).abs().max()) / B0_MASS < 1e-12
+    with pytest.raises(RuntimeError):
+        kstar.set_children(GenParticle("x", 1.0), GenParticle("y", 1.0))

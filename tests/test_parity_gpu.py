@@ -5,6 +5,9 @@ components cross zero, so 4-vectors are compared as |delta| / M_top (SURVEY.md s
 Both arithmetic variants are checked: ``exact`` (reference operation order) and the default fast one.
 """
 
+import json
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -12,6 +15,7 @@ import torch
 from oracle import genbod_numpy as orc
 from oracle.philox import uniform_table
 
+from .helpers import conditioning
 from .helpers import decays as D
 
 pytestmark = pytest.mark.gpu
@@ -24,18 +28,40 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
-def _check_weights(got, ref, tol, loose):
-    """Weights agree to ``tol`` relative to the scale of the array for every event, and element by element
-    for all but the rare ill-conditioned events (a two-body step within ~1e-4 of its threshold, where the
-    weight itself goes to zero and the reference's own arithmetic loses digits): those stay within ``loose``."""
-    scale = float(np.max(np.abs(ref)))
-    assert np.max(np.abs(got - ref)) <= tol * scale, np.max(np.abs(got - ref)) / scale
-    rel = np.abs(got - ref) / np.abs(ref)
-    assert np.mean(rel > tol) <= 1e-3, (np.mean(rel > tol), rel.max())
-    assert rel.max() <= loose, rel.max()
+_SOFT = bool(os.environ.get("PS_PARITY_NOASSERT"))  # calibration runs only: report the margins, assert nothing
+C_AMP = 8.0  # events are held to max(tol, C_AMP * eps * A), A = tests/helpers/conditioning.py (measured: see _report)
 
 
-def _compare(desc, n, *, exact, use_rng, boost=None, normalize=True, seed=1234, tol=TOL, loose=1e-8):
+def _report(label, **fields):
+    """PS_PARITY_REPORT=<file>: append the measured margins of every comparison (kept under profiles/)."""
+    path = os.environ.get("PS_PARITY_REPORT")
+    if path:
+        with open(path, "a") as fh:
+            fh.write(json.dumps({"case": label, **fields}) + "\n")
+
+
+def _check_weights(got, ref, tol, amp=None, label=""):
+    """Every event's weight agrees with the reference to ``max(tol, C_AMP * eps * A_i)`` relative, where ``A_i`` is the
+    event's own rounding amplification computed from the reference outputs (conditioning.py): a two-body step near its
+    threshold, where the weight itself goes to zero, or a mass re-derived from a boosted 4-vector.  There is no blanket
+    allowance: an event above ``tol`` must be explained by its own ``A_i``; how many there are and how far they sit
+    from the bound is reported."""
+    rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+    rel = np.where(ref == 0.0, np.abs(got), rel)
+    bound = np.full(ref.shape, tol) if amp is None else np.maximum(tol, C_AMP * conditioning.EPS * amp)
+    above = rel > tol
+    worst = int(np.argmax(rel / bound))
+    _report(label, n=int(ref.size), tol=tol, n_above_tol=int(above.sum()), max_rel=float(rel.max()),
+            max_rel_over_bound=float((rel / bound).max()),
+            max_rel_over_eps_amp=None if amp is None else float((rel / (conditioning.EPS * np.maximum(amp, 1.0))).max()),
+            min_amp_of_events_above_tol=None if amp is None or not above.any() else float(amp[above].min()),
+            max_amp=None if amp is None else float(amp.max()))
+    assert _SOFT or rel[worst] <= bound[worst], (
+        f"{label}: event {worst}: |dw|/w = {rel[worst]:.3e} > bound {bound[worst]:.3e} "
+        f"(A = {None if amp is None else amp[worst]:.4g}); {int(above.sum())} of {ref.size} events above {tol:g}")
+
+
+def _compare(desc, n, *, exact, use_rng, boost=None, normalize=True, seed=1234, tol=TOL, vec_tol=None):
     gen, tree = D.to_gen(desc), D.to_oracle(desc)
     draws = uniform_table(seed, 0, n, orc.n_draws(tree))
     boost_np = None if boost is None else np.asarray(boost, dtype=np.float64)
@@ -47,13 +73,17 @@ def _compare(desc, n, *, exact, use_rng, boost=None, normalize=True, seed=1234, 
         got = gen.generate(n, debug_uniforms=torch.as_tensor(draws), **kwargs)
     scale = float(desc[1]) if boost is None else float(np.max(boost_np[:, 3]))
     assert list(got[-1].keys()) == orc.output_names(tree)
-    _check_weights(_np(got[0]), ref[0], tol, loose)
+    amp = conditioning.amplification(desc, ref[-1], boost_np)
+    label = f"{desc[0]}/{len(ref[-1])}p/{'exact' if exact else 'fast'}/{'rng' if use_rng else 'dbg'}" + ("/boost" if boost is not None else "")
+    _check_weights(_np(got[0]), ref[0], tol, amp, label + "/w")
     if not normalize:
-        _check_weights(_np(got[1]), ref[1], tol, loose)
+        # the maximum weight has no threshold factor of its own (it is evaluated at the kinematic limits)
+        _check_weights(_np(got[1]), ref[1], tol, None if boost is None else amp, label + "/w_max")
     worst = 0.0
     for name, vec in ref[-1].items():
         worst = max(worst, float(np.max(np.abs(_np(got[-1][name]) - vec))) / scale)
-    assert worst <= tol, worst
+    _report(label + "/vec", worst_over_scale=worst, tol=vec_tol or tol)
+    assert _SOFT or worst <= (vec_tol or tol), worst
     return worst
 
 
@@ -80,15 +110,14 @@ def test_mixed_masses_unnormalized(exact):
 @pytest.mark.parametrize("kind", ["fixed", "gauss", "bw", "relbw"])
 def test_kstar_gamma(kind, exact):
     desc = D.kstar_gamma_desc(kind) if kind != "fixed" else D.kstar_gamma_desc("fixed", 0.0)
-    # resonance masses go through libm vs CUDA normcdfinv/atan/tan/log: allow a little more
-    _compare(desc, N, exact=exact, use_rng=False, tol=5e-12 if kind != "fixed" else TOL)
-    _compare(desc, N, exact=exact, use_rng=True, normalize=False, tol=5e-12 if kind != "fixed" else TOL)
+    _compare(desc, N, exact=exact, use_rng=False)
+    _compare(desc, N, exact=exact, use_rng=True, normalize=False)
 
 
 @pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
 @pytest.mark.parametrize("kinds", [("fixed", "fixed"), ("gauss", "gauss"), ("relbw", "relbw"), ("bw", "gauss")])
 def test_k1_gamma(kinds, exact):
-    _compare(D.k1_gamma_desc(*kinds), N, exact=exact, use_rng=False, tol=5e-12)
+    _compare(D.k1_gamma_desc(*kinds), N, exact=exact, use_rng=False)
 
 
 def _fonll_like_boost(n, mass, seed=1234):
@@ -104,35 +133,28 @@ def _fonll_like_boost(n, mass, seed=1234):
 @pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
 def test_boost_to_per_event(exact):
     boost = _fonll_like_boost(N, D.B0_MASS)
-    gamma2 = float(np.max(boost[:, 3]) / D.B0_MASS) ** 2
-    # flat tree: weights depend on the boost only through kin.mass(boost_to), identical in oracle and kernel;
-    # the boosted vectors carry the rounding of gamma ~ E/M (compared on the scale of the largest energy)
-    _compare(D.flat_desc(4), N, exact=exact, use_rng=False, boost=boost, tol=1e-12 * np.sqrt(gamma2) / 10)
+    gamma = float(np.max(boost[:, 3]) / D.B0_MASS)
+    # flat tree: the weights depend on the boost only through kin.mass(boost_to), the same expression in oracle and
+    # kernel: plain 1e-12.  The boosted vectors carry the rounding of gamma ~ E/M, compared on the scale of the
+    # largest energy: eps * gamma.
+    _compare(D.flat_desc(4), N, exact=exact, use_rng=False, boost=boost, vec_tol=max(TOL, 16 * conditioning.EPS * gamma))
     # chain: the reference re-derives each resonance mass as sqrt(E^2 - p^2) of its *boosted* 4-vector
-    # (phasespace.py:322 via 564), an expression whose rounding error grows like eps * gamma^2; oracle and
-    # kernel only share that noise up to the last bits of sin/cos, so the weights agree to ~1e-12 * gamma^2.
-    tol_w = 1e-12 * gamma2
-    gen, tree = D.to_gen(D.kstar_gamma_desc("gauss")), D.to_oracle(D.kstar_gamma_desc("gauss"))
-    draws = uniform_table(5, 0, N, orc.n_draws(tree))
-    ref_w, ref_wmax, ref_p = orc.generate(tree, N, draws, boost_to=boost, normalize_weights=False)
-    w, wmax, p = gen.generate(N, boost_to=torch.as_tensor(boost), normalize_weights=False, seed=5, exact=exact)
-    np.testing.assert_allclose(_np(wmax), ref_wmax, rtol=1e-11)
-    np.testing.assert_allclose(_np(w), ref_w, rtol=tol_w)
-    assert np.median(np.abs(_np(w) - ref_w) / ref_w) < 1e-11
-    scale = float(np.max(boost[:, 3]))
-    for name, vec in ref_p.items():  # grandchildren inherit the mass noise: ~1e-12 * gamma of the energy scale
-        assert np.max(np.abs(_np(p[name]) - vec)) / scale <= 1e-12 * np.sqrt(gamma2), name
-    # moderate boosts (gamma <= 20, an LHC B meson): plain tolerances hold
+    # (phasespace.py:322 via 564), an expression whose rounding error grows like eps * gamma^2 -- that is part of every
+    # event's own bound (conditioning.py), not a blanket tolerance
+    _compare(D.kstar_gamma_desc("gauss"), N, exact=exact, use_rng=True, boost=boost, normalize=False, seed=5,
+             vec_tol=max(TOL, 16 * conditioning.EPS * gamma))
+    # moderate boosts (gamma <= 20, an LHC B meson)
     slow = boost.copy()
     slow[:, :3] *= 20.0 * D.B0_MASS / np.maximum(np.linalg.norm(slow[:, :3], axis=1, keepdims=True), 20.0 * D.B0_MASS)
     slow[:, 3] = np.sqrt((slow[:, :3] ** 2).sum(1) + D.B0_MASS**2)
-    _compare(D.kstar_gamma_desc("gauss"), N, exact=exact, use_rng=True, boost=slow, normalize=False, tol=1e-9, loose=1e-6)
+    _compare(D.kstar_gamma_desc("gauss"), N, exact=exact, use_rng=True, boost=slow, normalize=False)
 
 
 @pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
 def test_boost_to_broadcast(exact):
     boost = _fonll_like_boost(1, D.B0_MASS, seed=5)
-    _compare(D.flat_desc(3), N, exact=exact, use_rng=False, boost=boost, tol=1e-11)
+    gamma = float(boost[0, 3] / D.B0_MASS)
+    _compare(D.flat_desc(3), N, exact=exact, use_rng=False, boost=boost, vec_tol=max(TOL, 16 * conditioning.EPS * gamma))
 
 
 def test_sharding_is_bit_identical():
@@ -233,11 +255,11 @@ def test_random_trees_jit(tree_seed):
     top_mass = 3.0 * sum(c[1] if c[4] else _node_floor(c) for c in desc[4]) + 1000.0
     desc = (desc[0], top_mass, "fixed", 0.0, desc[4])
     # Tolerance: the reference (and the oracle) re-derive the mass of every decaying particle as sqrt(E^2 - p^2) of
-    # its boosted 4-vector, which loses eps * gamma^2 per level; two or three levels of light
-    # intermediates push the weight differences to ~1e-10.  Far Cauchy tails also land within ~1e-4 of a threshold
-    # now and then (see _check_weights).
-    _compare(desc, 4000, exact=False, use_rng=True, tol=3e-10, loose=1e-6)
-    _compare(desc, 500, exact=True, use_rng=False, tol=3e-10, loose=1e-6)
+    # its boosted 4-vector, which loses eps * gamma^2 per level, and far Cauchy tails land within
+    # ~1e-4 of a threshold now and then: both are in each event's own bound (conditioning.py).  The 4-vectors of the
+    # particles below a light, fast intermediate inherit its mass noise on the scale of the top mass.
+    _compare(desc, 4000, exact=False, use_rng=True, vec_tol=3e-10)
+    _compare(desc, 500, exact=True, use_rng=False, vec_tol=3e-10)
 
 
 from .helpers import reference_cases as R  # noqa: E402
@@ -257,13 +279,17 @@ def test_debug_mode_matches_reference_source(case, exact):
     w, w_max, parts = gen.generate(n, boost_to=boost, normalize_weights=False, exact=exact,
                                    debug_uniforms=torch.as_tensor(ref["draws"]))
     assert list(parts) == ref["names"]
-    # a boosted parent re-derives its mass as sqrt(E^2 - p^2): eps * gamma^2 (see test_boost_to_per_event)
-    tol = TOL if ref["boost"] is None else 2e-10
-    _check_weights(_np(w), ref["weights"], tol, 1e-8)
-    _check_weights(_np(w_max), ref["weights_max"], tol, 1e-8)
+    # 1e-12 for every case, boosted or not; an event beyond it must be explained by its own amplification (a boosted
+    # resonance re-derives its mass as sqrt(E^2 - p^2): eps * gamma^2, conditioning.py) -- flat decays have none
+    ref_parts = {name: ref["particles"][k] for k, name in enumerate(ref["names"])}
+    amp = conditioning.amplification(R.CASES[case], ref_parts, ref["boost"])
+    label = f"refsrc/{case}/{'exact' if exact else 'fast'}"
+    _check_weights(_np(w), ref["weights"], TOL, amp, label + "/w")
+    _check_weights(_np(w_max), ref["weights_max"], TOL, None if ref["boost"] is None else amp, label + "/w_max")
     scale = D.B0_MASS if ref["boost"] is None else float(np.max(ref["boost"][:, 3]))
-    for k, name in enumerate(ref["names"]):
-        assert np.max(np.abs(_np(parts[name]) - ref["particles"][k])) <= TOL * scale, name
+    worst = max(float(np.max(np.abs(_np(parts[name]) - ref_parts[name]))) / scale for name in ref["names"])
+    _report(label + "/vec", worst_over_scale=worst, tol=TOL)
+    assert _SOFT or worst <= TOL, worst
 
 
 def _leaf(name, mass):
@@ -294,4 +320,4 @@ def test_edge_trees(name):
     """Shapes and scales off the beaten path (all but the last are NVRTC-compiled): massless products, GeV units, the
     largest tree the parameter block holds, a depth-five chain through all three samplers, a decay at threshold."""
     desc, n, tol = _EDGE_TREES[name]
-    _compare(desc, n, exact=False, use_rng=True, tol=tol, loose=1e-6)
+    _compare(desc, n, exact=False, use_rng=True, vec_tol=tol)

@@ -26,7 +26,7 @@ err = torch.zeros((1,), dtype=torch.int32, device=dev)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 for rep in range(3):
     ev[0].record()
-    _lib.check(lib.ps_unweight_mask(comp.handle, 1, 0, n, bound, _ptr(mask), _ptr(err), 0, stream))
+    _lib.check(lib.ps_unweight_mask(comp.handle, 1, 0, n, bound, _ptr(mask), None, _ptr(err), 0, stream))
     ev[1].record()
     _lib.check(lib.ps_unweight_scan(_ptr(mask), n, _ptr(offsets), _ptr(total), stream))
     ev[2].record()
