@@ -52,7 +52,7 @@ except AttributeError:  # pragma: no cover
         return torch.cuda.current_stream(index).cuda_stream
 
 
-def _check_out(t, name, shape, device, dtype=torch.float64, pinned_host=False):
+def _check_out(t, name, shape, device, dtype=torch.float64, pinned_host=False, planes=False):
     """A caller-supplied output buffer goes to the C ABI as a bare pointer: anything but the exact shape, dtype,
     device and a dense layout would make the kernel (or the D2H copies) write out of bounds."""
     if t is None:
@@ -63,7 +63,12 @@ def _check_out(t, name, shape, device, dtype=torch.float64, pinned_host=False):
         raise ValueError(f"out[{name!r}] must have shape {tuple(shape)}, not {tuple(t.shape)}")
     if t.dtype != dtype:
         raise ValueError(f"out[{name!r}] must have dtype {dtype}, not {t.dtype}")
-    if not t.is_contiguous():
+    if planes and t.ndim == 3 and t.shape[0] > 1 and t.shape[1] > 0:
+        # (P, n, 4): dense (n, 4) planes; the distance between planes may exceed 4 n (a slab with spare capacity)
+        if t.stride(2) != 1 or t.stride(1) != 4 or t.stride(0) < 4 * t.shape[1] or t.stride(0) % 4:
+            raise ValueError(f"out[{name!r}] must consist of dense (n, 4) planes at a stride that is a multiple of 4 "
+                             f"and at least 4 n; strides are {tuple(t.stride())}")
+    elif not t.is_contiguous():
         raise ValueError(f"out[{name!r}] must be contiguous")
     if pinned_host:
         if t.device.type != "cpu":
@@ -214,7 +219,7 @@ class CompiledDecay:
         weights, particles = out.get("weights"), out.get("particles")
         weights_max = out.get("weights_max") if not normalize_weights else None
         _check_out(weights, "weights", (n,), device)
-        _check_out(particles, "particles", (self.n_particles, n, 4), device)
+        _check_out(particles, "particles", (self.n_particles, n, 4), device, planes=True)
         _check_out(weights_max, "weights_max", (n,), device)
         _check_out(stats, "stats", (4,), device)
         _check_out(err, "err", (1,), device, dtype=torch.int32)

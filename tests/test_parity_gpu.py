@@ -29,7 +29,7 @@ def _np(t):
 
 
 _SOFT = bool(os.environ.get("PS_PARITY_NOASSERT"))  # calibration runs only: report the margins, assert nothing
-C_AMP = 8.0  # events are held to max(tol, C_AMP * eps * A), A = tests/helpers/conditioning.py (measured: see _report)
+C_AMP = 8.0  # events are held to max(tol, C_AMP * eps * A), A = tests/helpers/conditioning.py (measured margins: _report)
 
 
 def _report(label, **fields):
@@ -40,28 +40,49 @@ def _report(label, **fields):
             fh.write(json.dumps({"case": label, **fields}) + "\n")
 
 
-def _check_weights(got, ref, tol, amp=None, label=""):
-    """Every event's weight agrees with the reference to ``max(tol, C_AMP * eps * A_i)`` relative, where ``A_i`` is the
-    event's own rounding amplification computed from the reference outputs (conditioning.py): a two-body step near its
-    threshold, where the weight itself goes to zero, or a mass re-derived from a boosted 4-vector.  There is no blanket
-    allowance: an event above ``tol`` must be explained by its own ``A_i``; how many there are and how far they sit
-    from the bound is reported."""
-    rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
-    rel = np.where(ref == 0.0, np.abs(got), rel)
-    bound = np.full(ref.shape, tol) if amp is None else np.maximum(tol, C_AMP * conditioning.EPS * amp)
-    above = rel > tol
-    worst = int(np.argmax(rel / bound))
-    _report(label, n=int(ref.size), tol=tol, n_above_tol=int(above.sum()), max_rel=float(rel.max()),
-            max_rel_over_bound=float((rel / bound).max()),
-            max_rel_over_eps_amp=None if amp is None else float((rel / (conditioning.EPS * np.maximum(amp, 1.0))).max()),
-            min_amp_of_events_above_tol=None if amp is None or not above.any() else float(amp[above].min()),
-            max_amp=None if amp is None else float(amp.max()))
-    assert _SOFT or rel[worst] <= bound[worst], (
-        f"{label}: event {worst}: |dw|/w = {rel[worst]:.3e} > bound {bound[worst]:.3e} "
-        f"(A = {None if amp is None else amp[worst]:.4g}); {int(above.sum())} of {ref.size} events above {tol:g}")
+def _check_events(err, bound, amp, tol, label):
+    """``err`` (per event: relative weight difference, or 4-vector difference on the event's scale) stays below the
+    event's own ``bound`` = max(tol, c * A_i) (conditioning.py).  There is no blanket allowance: an event above ``tol``
+    must be explained by its own amplification A_i -- a two-body step near its threshold, where the weight itself goes
+    to zero, a mass re-derived from a boosted 4-vector, a sampled mass.  How many such events there are and how close
+    the worst one comes to its bound is reported."""
+    above = err > tol
+    worst = int(np.argmax(err / bound))
+    _report(label, n=int(err.size), tol=tol, n_above_tol=int(above.sum()), max_err=float(err.max()),
+            max_err_over_bound=float((err / bound).max()),
+            max_err_over_eps_amp=float((err / (conditioning.EPS * np.maximum(amp, 1.0))).max()),
+            min_amp_of_events_above_tol=float(amp[above].min()) if above.any() else None, max_amp=float(amp.max()))
+    assert _SOFT or err[worst] <= bound[worst], (
+        f"{label}: event {worst}: error {err[worst]:.3e} > bound {bound[worst]:.3e} (A = {amp[worst]:.4g}); "
+        f"{int(above.sum())} of {err.size} events above {tol:g}")
 
 
-def _compare(desc, n, *, exact, use_rng, boost=None, normalize=True, seed=1234, tol=TOL, vec_tol=None):
+def _rel(got, ref):
+    return np.where(ref == 0.0, np.abs(got), np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
+
+
+def _check_against(desc, got, ref, boost_np, label, tol=TOL):
+    """``got`` / ``ref``: ``(weights, [weights_max,] {name: (n, 4)})`` of the kernel and of the reference / oracle."""
+    parts_ref = ref[-1]
+    n = ref[0].shape[0]
+    amp, w_bound, v_bound = conditioning.event_bounds(desc, parts_ref, boost_np, tol=tol, c_amp=C_AMP)
+    _check_events(_rel(_np(got[0]), ref[0]), w_bound, amp, tol, label + "/w")
+    if len(ref) == 3:
+        # the maximum weight is evaluated at the kinematic limits: no threshold factor of its own.  Under boost_to it
+        # depends on the event through kin.mass(boost_to), the same expression in reference and kernel.
+        wmax_err = _rel(_np(got[1]), ref[1])
+        _check_events(wmax_err, np.full(n, tol), np.ones(n), tol, label + "/w_max")
+    if boost_np is None:
+        scale = np.full(n, float(desc[1]))
+    else:
+        scale = np.broadcast_to(np.asarray(boost_np, dtype=np.float64).reshape(-1, 4)[:, 3], (n,))
+    v_err = np.zeros(n)
+    for name, vec in parts_ref.items():
+        v_err = np.maximum(v_err, np.max(np.abs(_np(got[-1][name]) - vec), axis=1) / scale)
+    _check_events(v_err, v_bound, amp, tol, label + "/vec")
+
+
+def _compare(desc, n, *, exact, use_rng, boost=None, normalize=True, seed=1234, tol=TOL):
     gen, tree = D.to_gen(desc), D.to_oracle(desc)
     draws = uniform_table(seed, 0, n, orc.n_draws(tree))
     boost_np = None if boost is None else np.asarray(boost, dtype=np.float64)
@@ -71,20 +92,9 @@ def _compare(desc, n, *, exact, use_rng, boost=None, normalize=True, seed=1234, 
         got = gen.generate(n, seed=seed, **kwargs)
     else:
         got = gen.generate(n, debug_uniforms=torch.as_tensor(draws), **kwargs)
-    scale = float(desc[1]) if boost is None else float(np.max(boost_np[:, 3]))
     assert list(got[-1].keys()) == orc.output_names(tree)
-    amp = conditioning.amplification(desc, ref[-1], boost_np)
     label = f"{desc[0]}/{len(ref[-1])}p/{'exact' if exact else 'fast'}/{'rng' if use_rng else 'dbg'}" + ("/boost" if boost is not None else "")
-    _check_weights(_np(got[0]), ref[0], tol, amp, label + "/w")
-    if not normalize:
-        # the maximum weight has no threshold factor of its own (it is evaluated at the kinematic limits)
-        _check_weights(_np(got[1]), ref[1], tol, None if boost is None else amp, label + "/w_max")
-    worst = 0.0
-    for name, vec in ref[-1].items():
-        worst = max(worst, float(np.max(np.abs(_np(got[-1][name]) - vec))) / scale)
-    _report(label + "/vec", worst_over_scale=worst, tol=vec_tol or tol)
-    assert _SOFT or worst <= (vec_tol or tol), worst
-    return worst
+    _check_against(desc, got, ref, boost_np, label, tol)
 
 
 @pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
@@ -133,16 +143,13 @@ def _fonll_like_boost(n, mass, seed=1234):
 @pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
 def test_boost_to_per_event(exact):
     boost = _fonll_like_boost(N, D.B0_MASS)
-    gamma = float(np.max(boost[:, 3]) / D.B0_MASS)
     # flat tree: the weights depend on the boost only through kin.mass(boost_to), the same expression in oracle and
-    # kernel: plain 1e-12.  The boosted vectors carry the rounding of gamma ~ E/M, compared on the scale of the
-    # largest energy: eps * gamma.
-    _compare(D.flat_desc(4), N, exact=exact, use_rng=False, boost=boost, vec_tol=max(TOL, 16 * conditioning.EPS * gamma))
+    # kernel; the boosted vectors carry the reference's own gamma = 1/sqrt(1 - beta^2) rounding (conditioning.py)
+    _compare(D.flat_desc(4), N, exact=exact, use_rng=False, boost=boost)
     # chain: the reference re-derives each resonance mass as sqrt(E^2 - p^2) of its *boosted* 4-vector
     # (phasespace.py:322 via 564), an expression whose rounding error grows like eps * gamma^2 -- that is part of every
     # event's own bound (conditioning.py), not a blanket tolerance
-    _compare(D.kstar_gamma_desc("gauss"), N, exact=exact, use_rng=True, boost=boost, normalize=False, seed=5,
-             vec_tol=max(TOL, 16 * conditioning.EPS * gamma))
+    _compare(D.kstar_gamma_desc("gauss"), N, exact=exact, use_rng=True, boost=boost, normalize=False, seed=5)
     # moderate boosts (gamma <= 20, an LHC B meson)
     slow = boost.copy()
     slow[:, :3] *= 20.0 * D.B0_MASS / np.maximum(np.linalg.norm(slow[:, :3], axis=1, keepdims=True), 20.0 * D.B0_MASS)
@@ -153,8 +160,7 @@ def test_boost_to_per_event(exact):
 @pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
 def test_boost_to_broadcast(exact):
     boost = _fonll_like_boost(1, D.B0_MASS, seed=5)
-    gamma = float(boost[0, 3] / D.B0_MASS)
-    _compare(D.flat_desc(3), N, exact=exact, use_rng=False, boost=boost, vec_tol=max(TOL, 16 * conditioning.EPS * gamma))
+    _compare(D.flat_desc(3), N, exact=exact, use_rng=False, boost=boost)
 
 
 def test_sharding_is_bit_identical():
@@ -256,10 +262,10 @@ def test_random_trees_jit(tree_seed):
     desc = (desc[0], top_mass, "fixed", 0.0, desc[4])
     # Tolerance: the reference (and the oracle) re-derive the mass of every decaying particle as sqrt(E^2 - p^2) of
     # its boosted 4-vector, which loses eps * gamma^2 per level, and far Cauchy tails land within
-    # ~1e-4 of a threshold now and then: both are in each event's own bound (conditioning.py).  The 4-vectors of the
-    # particles below a light, fast intermediate inherit its mass noise on the scale of the top mass.
-    _compare(desc, 4000, exact=False, use_rng=True, vec_tol=3e-10)
-    _compare(desc, 500, exact=True, use_rng=False, vec_tol=3e-10)
+    # ~1e-4 of a threshold now and then: both are in each event's own bound (conditioning.py), for the weights and for
+    # the 4-vectors of the particles below such an intermediate.
+    _compare(desc, 4000, exact=False, use_rng=True)
+    _compare(desc, 500, exact=True, use_rng=False)
 
 
 from .helpers import reference_cases as R  # noqa: E402
@@ -282,14 +288,8 @@ def test_debug_mode_matches_reference_source(case, exact):
     # 1e-12 for every case, boosted or not; an event beyond it must be explained by its own amplification (a boosted
     # resonance re-derives its mass as sqrt(E^2 - p^2): eps * gamma^2, conditioning.py) -- flat decays have none
     ref_parts = {name: ref["particles"][k] for k, name in enumerate(ref["names"])}
-    amp = conditioning.amplification(R.CASES[case], ref_parts, ref["boost"])
-    label = f"refsrc/{case}/{'exact' if exact else 'fast'}"
-    _check_weights(_np(w), ref["weights"], TOL, amp, label + "/w")
-    _check_weights(_np(w_max), ref["weights_max"], TOL, None if ref["boost"] is None else amp, label + "/w_max")
-    scale = D.B0_MASS if ref["boost"] is None else float(np.max(ref["boost"][:, 3]))
-    worst = max(float(np.max(np.abs(_np(parts[name]) - ref_parts[name]))) / scale for name in ref["names"])
-    _report(label + "/vec", worst_over_scale=worst, tol=TOL)
-    assert _SOFT or worst <= TOL, worst
+    _check_against(R.CASES[case], (w, w_max, parts), (ref["weights"], ref["weights_max"], ref_parts), ref["boost"],
+                   f"refsrc/{case}/{'exact' if exact else 'fast'}")
 
 
 def _leaf(name, mass):
@@ -297,8 +297,8 @@ def _leaf(name, mass):
 
 
 _EDGE_TREES = {
-    # massless products allow arbitrarily light subsystems: the boosts then amplify rounding by gamma (1e-9 here)
-    "three_massless": (D.flat_desc(3, top=100.0, masses=[0.0, 0.0, 0.0]), 2000, 1e-9),
+    # massless products allow arbitrarily light subsystems: the boosts then amplify rounding by gamma^2 (conditioning.py)
+    "three_massless": (D.flat_desc(3, top=100.0, masses=[0.0, 0.0, 0.0]), 2000, 1e-12),
     "gev_units": (("B", 5.27958, "fixed", 0.0, [
         ("K*", 0.89581, "relbw", 0.0474, [_leaf("K", 0.493677), _leaf("pi", 0.13957)]), _leaf("g", 0.0)]), 2000, 1e-12),
     "sixteen_body": (D.flat_desc(16, top=20000.0, masses=[139.57] * 16), 1000, 1e-12),
@@ -310,7 +310,7 @@ _EDGE_TREES = {
                     ("E", 900.0, "fixed", 0.0, [_leaf("e1", 139.57), _leaf("e2", 493.677)]), _leaf("d2", 139.57)]),
                 _leaf("c2", 105.66)]),
             _leaf("b2", 0.0)]),
-        _leaf("a2", 938.272)]), 2000, 1e-11),
+        _leaf("a2", 938.272)]), 2000, 1e-12),
     "one_kev_above_threshold": (D.flat_desc(3, top=3 * D.PION_MASS + 1e-3, masses=[D.PION_MASS] * 3), 2000, 1e-12),
 }
 
@@ -320,4 +320,4 @@ def test_edge_trees(name):
     """Shapes and scales off the beaten path (all but the last are NVRTC-compiled): massless products, GeV units, the
     largest tree the parameter block holds, a depth-five chain through all three samplers, a decay at threshold."""
     desc, n, tol = _EDGE_TREES[name]
-    _compare(desc, n, exact=False, use_rng=True, vec_tol=tol)
+    _compare(desc, n, exact=False, use_rng=True, tol=tol)

@@ -10,6 +10,9 @@ oracle (scipy's truncated normal and Cauchy; adaptive quadrature of the document
 point by point against the oracle's restatement fed the same uniforms.
 """
 
+import json
+import os
+
 import numpy as np
 import pytest
 import scipy.integrate
@@ -20,6 +23,8 @@ import phasespace_b200 as ps
 from oracle import genbod_numpy as orc
 from oracle.philox import uniform_table
 from phasespace_b200.fromdecay import mass_functions as mf
+
+from .helpers import conditioning
 
 pytestmark = pytest.mark.gpu
 
@@ -71,7 +76,15 @@ def test_standalone_sampler_distribution(kind, case):
     # and point by point against the oracle's restatement of the same inverse CDF, same uniforms (Philox stream 2)
     u = uniform_table(11, 0, N, 1, stream=2)[:, 0]
     ref = orc.sample_mass(ORC_KIND[kind], m, w, np.full(N, lo), np.full(N, hi), u)
-    assert np.max(np.abs(x - ref)) / hi < 5e-12
+    rel = np.abs(x - ref) / np.maximum(np.abs(ref), 1e-300)
+    worst, q999 = float(rel.max()), float(np.quantile(rel, 0.999))
+    if os.environ.get("PS_PARITY_REPORT"):
+        with open(os.environ["PS_PARITY_REPORT"], "a") as fh:
+            fh.write(json.dumps({"case": f"sampler/{kind}/{case}", "max_rel_mass_difference": worst, "q999": q999}) + "\n")
+    # An inverse CDF is ill-conditioned in the far tails (dx = du / pdf(x)): the largest differences (measured: 1.6e-12
+    # for the relativistic Breit-Wigner on [1000, 5279], 21 widths above the pole) sit there.  The bulk agrees to the
+    # constant the generator parity bounds use (tests/helpers/conditioning.py).
+    assert worst < 5e-12 and q999 < conditioning.MASS_NOISE, (worst, q999)
 
 
 @pytest.mark.parametrize("case", CASES[:5], ids=lambda c: f"m{c[0]:g}_w{c[1]:g}_{c[2]:g}_{c[3]:g}")
