@@ -72,7 +72,6 @@ struct Registry {
     std::mutex mu;
     std::map<KernelKey, const void*> aot;
     std::map<KernelKey, const void*> jit;           // cudaKernel_t handles of NVRTC-built kernels
-    std::map<const void*, int> blocks_per_sm;       // occupancy cache
 };
 Registry& registry() {
     static Registry r;
@@ -101,6 +100,10 @@ struct ps_tree {
     double w_max = NAN;
     std::string signature;
     PsParams base;  // constant part of the parameter block
+    // resolved kernels of this tree, [variant][boost][dbg][exact]: a small call (1e6 events last ~15 us on a B200) should
+    // not pay for a mutex and a map lookup keyed on a hundred-character string every time
+    mutable std::atomic<const void*> kernel_cache[3][2][2][2] = {};
+    mutable std::atomic<int> blocks_per_sm_cache[3][2][2][2] = {};
 };
 
 namespace {
@@ -568,7 +571,34 @@ int jit_compile(const KernelKey& key, const void** fn_out) {
     return rc_load;
 }
 
+int sm_count(int* out) {
+    static std::atomic<int> cache[64] = {};
+    int dev = 0;
+    PS_CUDA(cudaGetDevice(&dev));
+    int sms = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
+    if (sms == 0) {
+        PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) cache[dev].store(sms, std::memory_order_relaxed);
+    }
+    *out = sms;
+    return 0;
+}
+
+int get_kernel_slow(const ps_tree* t, int variant, int boost, int dbg, int exact, const void** fn);
+
 int get_kernel(const ps_tree* t, int variant, int boost, int dbg, int exact, const void** fn) {
+    std::atomic<const void*>& slot = t->kernel_cache[variant][boost ? 1 : 0][dbg ? 1 : 0][exact ? 1 : 0];
+    const void* cached = slot.load(std::memory_order_acquire);
+    if (cached) {
+        *fn = cached;
+        return 0;
+    }
+    int rc = get_kernel_slow(t, variant, boost ? 1 : 0, dbg ? 1 : 0, exact ? 1 : 0, fn);
+    if (rc == 0) slot.store(*fn, std::memory_order_release);
+    return rc;
+}
+
+int get_kernel_slow(const ps_tree* t, int variant, int boost, int dbg, int exact, const void** fn) {
     KernelKey key{t->signature, variant, boost, dbg, exact};
     Registry& r = registry();
     std::lock_guard<std::mutex> lock(r.mu);
@@ -584,24 +614,19 @@ int get_kernel(const ps_tree* t, int variant, int boost, int dbg, int exact, con
 // Launch shape (see genbod_body): a persistent grid of SM count x resident CTAs with a static tile stride;
 // for trees with at most PS_CHUNKED_MAX_P particles (memory-bound) a covering grid with up to 16
 // consecutive tiles per CTA.
-int pick_grid(const ps_tree* t, const void* fn, long long n_events, int* grid, int* tiles_per_cta) {
-    Registry& r = registry();
-    int per_sm = 0;
-    {
-        std::lock_guard<std::mutex> lock(r.mu);
-        auto it = r.blocks_per_sm.find(fn);
-        if (it != r.blocks_per_sm.end()) per_sm = it->second;
-    }
-    int dev = 0, sms = 0;
-    PS_CUDA(cudaGetDevice(&dev));
-    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+int pick_grid(const ps_tree* t, const void* fn, int boost, int dbg, int exact, long long n_events, int* grid,
+              int* tiles_per_cta) {
+    std::atomic<int>& slot = t->blocks_per_sm_cache[PS_VARIANT_GENERATE][boost ? 1 : 0][dbg ? 1 : 0][exact ? 1 : 0];
+    int per_sm = slot.load(std::memory_order_relaxed);
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc) return rc;
     if (per_sm == 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PS_BLOCK, 0) != cudaSuccess || per_sm < 1) {
             (void)cudaGetLastError();
             per_sm = 2;
         }
-        std::lock_guard<std::mutex> lock(r.mu);
-        r.blocks_per_sm[fn] = per_sm;
+        slot.store(per_sm, std::memory_order_relaxed);
     }
     const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
     int k = 0;
@@ -665,10 +690,11 @@ int launch_generate(const ps_tree* t, PsParams& p, uint32_t flags, void* stream)
     if (!aligned32(p.particles) || (p.particle_stride & 3) || p.particle_stride < 4 * p.n_events)
         return fail(PS_E_INVALID, "particles must be 32-byte aligned with particle_stride a multiple of 4 and >= 4*n_events");
     const void* fn = nullptr;
-    int rc = get_kernel(t, PS_VARIANT_GENERATE, p.boost_to ? 1 : 0, p.dbg_u ? 1 : 0, (flags & PS_GEN_EXACT) ? 1 : 0, &fn);
+    const int boost = p.boost_to ? 1 : 0, dbg = p.dbg_u ? 1 : 0, exact = (flags & PS_GEN_EXACT) ? 1 : 0;
+    int rc = get_kernel(t, PS_VARIANT_GENERATE, boost, dbg, exact, &fn);
     if (rc) return rc;
     int grid = 1;
-    rc = pick_grid(t, fn, p.n_events, &grid, &p.tiles_per_cta);
+    rc = pick_grid(t, fn, boost, dbg, exact, p.n_events, &grid, &p.tiles_per_cta);
     if (rc) return rc;
     void* args[] = {&p};
     PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, 0, (cudaStream_t)stream));
@@ -964,9 +990,9 @@ extern "C" int ps_unweight_mask(const ps_tree* tree, uint64_t seed, uint64_t fir
     const void* fn = nullptr;
     rc = get_kernel(tree, PS_VARIANT_MASK, 0, 0, (flags & PS_GEN_EXACT) ? 1 : 0, &fn);
     if (rc) return rc;
-    int dev = 0, sms = 0;
-    PS_CUDA(cudaGetDevice(&dev));
-    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int sms = 0;
+    rc = sm_count(&sms);
+    if (rc) return rc;
     const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
     int grid = (int)((long long)sms * 8 < tiles ? (long long)sms * 8 : tiles);
     void* args[] = {&p, &w_bound, &mask, &overflow};
@@ -993,9 +1019,8 @@ extern "C" int ps_unweight_index(const uint32_t* mask, const int64_t* tile_offse
                                  int64_t* event_index, void* stream) {
     if (!mask || !tile_offsets || !event_index) return fail(PS_E_INVALID, "null argument");
     if (n_events == 0) return 0;
-    int dev = 0, sms = 0;
-    PS_CUDA(cudaGetDevice(&dev));
-    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int sms = 0;
+    if (int rc = sm_count(&sms)) return rc;
     const long long n_words = (n_events + 31) / 32;
     const long long ctas = (n_words + PS_BLOCK - 1) / PS_BLOCK;
     const long long grid = (long long)sms * 8 < ctas ? (long long)sms * 8 : ctas;
@@ -1037,9 +1062,9 @@ extern "C" int ps_histogram(const ps_tree* tree, uint64_t seed, uint64_t first_e
     rc = get_kernel(tree, PS_VARIANT_HIST, boost_to ? 1 : 0, 0, (flags & PS_GEN_EXACT) ? 1 : 0, &fn);
     if (rc) return rc;
     if (smem > 48 * 1024) PS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 0, per_sm = 0;
-    PS_CUDA(cudaGetDevice(&dev));
-    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int sms = 0, per_sm = 0;
+    rc = sm_count(&sms);
+    if (rc) return rc;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PS_BLOCK, smem) != cudaSuccess || per_sm < 1) {
         (void)cudaGetLastError();
         per_sm = 1;

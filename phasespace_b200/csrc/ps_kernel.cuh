@@ -121,10 +121,16 @@ struct WmaxAcc {
 // the seed with twenty uniform-datapath additions per tile.  Measured: flat four-body decay 2.61 -> 2.54 ms per 1e8 events
 // (578 -> 545 instructions per loop iteration), but the memory-bound three-body decay 1.562 -> 1.577 ms (four more
 // registers, a different store schedule), so the small trees keep the seed form (use_keyed_philox).
-template <int P, bool DBG, bool WONLY = false, bool KEYED = true>
+// EARLY: the children of a top particle that decays at rest through the top-down path (genbod_topdown) are final as soon
+// as they are formed and are stored right away (out_row / out_stride) instead of being held until the end of the event.
+template <int P, bool DBG, bool WONLY = false, bool KEYED = true, bool EARLY = false>
 struct Ctx {
     static constexpr bool wonly = WONLY && !PS_EXACT;
+    static constexpr bool early_store = EARLY && !PS_EXACT;
     double px[P], py[P], pz[P], en[P], ms[P];
+    double* out_row;        // EARLY: row of this event in particle plane 0
+    long long out_stride;   // EARLY: doubles between planes
+    unsigned int wd[4];     // descending access (mantissa_desc): the first block of the column consumed last
     WmaxAcc wacc;  // 1 / (product of the two-body momenta of the event), wonly
     unsigned long long seed, event;
     const unsigned int* keys;  // PsParams::philox_keys
@@ -154,6 +160,54 @@ struct Ctx {
         unsigned int lo, hiword;
         field_words<bit0 - 128 * FB>(x, lo, hiword);
         return __hiloint2double((int)hiword, (int)lo);
+    }
+    // The same for draws consumed in DESCENDING column order (the top-down path forms the last particle first), from
+    // column TOPCOL down: the block kept (wd) is the one that holds the first bit of the column consumed last, and the
+    // block the ascending phase stopped in (index ASC, still in w) is reused when the descent reaches it.
+    template <int COL, int TOPCOL, int ASC>
+    __device__ __forceinline__ double mantissa_desc() {
+        constexpr int bit0 = PS_UNIFORM_BITS * COL;
+        constexpr int FB = bit0 / 128, LB = (bit0 + PS_UNIFORM_BITS - 1) / 128;
+        constexpr int HELD = COL == TOPCOL ? -1 : (PS_UNIFORM_BITS * (COL + 1)) / 128;
+        unsigned int x[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if constexpr (LB > FB) {
+            if constexpr (LB == HELD) {
+                x[4] = wd[0], x[5] = wd[1], x[6] = wd[2], x[7] = wd[3];
+            } else {
+                const Philox4 r = KEYED ? philox4x32_10_keyed(keys, event, LB, 0u) : philox4x32_10(seed, event, LB, 0u);
+                x[4] = r.w[0], x[5] = r.w[1], x[6] = r.w[2], x[7] = r.w[3];
+            }
+        }
+        if constexpr (FB == HELD) {
+            x[0] = wd[0], x[1] = wd[1], x[2] = wd[2], x[3] = wd[3];
+        } else if constexpr (FB == ASC) {
+            x[0] = wd[0] = w[0], x[1] = wd[1] = w[1], x[2] = wd[2] = w[2], x[3] = wd[3] = w[3];
+        } else {
+            const Philox4 r = KEYED ? philox4x32_10_keyed(keys, event, FB, 0u) : philox4x32_10(seed, event, FB, 0u);
+            x[0] = wd[0] = r.w[0], x[1] = wd[1] = r.w[1], x[2] = wd[2] = r.w[2], x[3] = wd[3] = r.w[3];
+        }
+        unsigned int lo, hiword;
+        field_words<bit0 - 128 * FB>(x, lo, hiword);
+        return __hiloint2double((int)hiword, (int)lo);
+    }
+    template <int COL, int TOPCOL, int ASC>
+    __device__ __forceinline__ double next_cos_desc() {
+        if constexpr (DBG)
+            return 2.0 * dbg_row[COL] - 1.0;
+        else
+            return fma(mantissa_desc<COL, TOPCOL, ASC>(), 4.0, -5.0);
+    }
+    template <int COL, int TOPCOL, int ASC>
+    __device__ __forceinline__ void next_turn_desc(double& y, double& u2) {
+        if constexpr (DBG) {
+            const double u = dbg_row[COL];
+            y = fma(u, 4.0, PS_TURN_MAGIC);
+            u2 = u + u;
+        } else {
+            const double d = mantissa_desc<COL, TOPCOL, ASC>();
+            y = fma(d, 8.0, PS_TURN_MAGIC - 8.0);
+            u2 = fma(d, 4.0, -4.0);
+        }
     }
     // the uniform u = 2 d - 2 itself
     template <int COL>
@@ -420,6 +474,205 @@ __device__ __forceinline__ void genbod_steps_fast(C& c, const double* pd, const 
     (genbod_step_fast<N, KM1 + 1, AB0 + 2 * KM1>(c, pd, ra, enew, esub, x, y, z, e), ...);
 }
 
+// ------------------------------------------------------------------ stores
+// One 256-bit store per particle per thread: a warp writes 32 consecutive 32-byte rows = 1 KiB
+// contiguous, i.e. eight full 128-byte lines per instruction (STG.E.ENL2.256 on sm_100a; PTX ISA 8.8,
+// CUDA >= 12.9).  Older NVRTC versions (PTX 8.7) fall back to two 128-bit halves.
+#if defined(__CUDACC_VER_MAJOR__) && (__CUDACC_VER_MAJOR__ * 100 + __CUDACC_VER_MINOR__ >= 1209)
+#define PS_HAVE_V4F64 1
+#else
+#define PS_HAVE_V4F64 0
+#endif
+__device__ __forceinline__ void store_row(double* p, double a, double b, double c, double d) {
+#if PS_HAVE_V4F64
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#else
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p + 2), "d"(c), "d"(d) : "memory");
+#endif
+}
+__device__ __forceinline__ void load_row(const double* p, double& a, double& b, double& c, double& d) {
+#if PS_HAVE_V4F64
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#else
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(d) : "l"(p + 2));
+#endif
+}
+
+// ------------------------------------------------------------------ top-down formulation for many-body nodes
+// The steps above touch every particle formed so far in every later step: (n(n+1)/2 - 1) rotations and (n(n-1)/2 - 1)
+// boosts of a particle, 12 fp64 instructions per particle and step.  The same events come out of ONE accumulated
+// Lorentz matrix when the steps are taken from the top down: with R_K the rotation and B_K the boost of step K,
+//     p_K = M_K v_K,   M_K = R_{N-1} B_{N-2} R_{N-2} ... B_K R_K = M_{K+1} B_K R_K,   v_K = (0, -pd[K-1], 0, E_K),
+// so each step costs one update of the matrix (three mixes of two columns, 48 instructions) and one product with a
+// vector that has two non-zero components (8), whatever K -- 56 per step against 12 K + 8.  By the count that pays from
+// eight bodies on, by the clock from nine (ten bodies: 434 instead of 568 instructions for the rotations and boosts), and a particle is final --
+// stored, its registers free -- as soon as it is formed, instead of living through every later step.  The draws are
+// the reference's, column for column (phasespace.py:444-451); they are merely consumed last pair first.
+// Measured on a B200 (5e7 events, ms per launch, bottom-up -> top-down): 8 bodies 3.46 -> 3.47, 9 bodies 4.39 -> 4.07,
+// 10 bodies 5.15 -> 4.67; six bodies lose 3 %.
+#ifndef PS_TOPDOWN_MIN_N
+#define PS_TOPDOWN_MIN_N 9
+#endif
+
+// quantities of the two-body step a -> b + cc: momentum, 1/a, energy of cc and of the subsystem b in the rest frame of a
+__device__ __forceinline__ void two_body(double a, double b, double cc, double& pd, double& ra, double& enew, double& esub) {
+    const double amb = a - b, apb = a + b;
+    const double xx = (amb - cc) * (apb + cc) * (amb + cc) * (apb - cc);
+    ra = rcp_pos1(a);
+    const double hra = 0.5 * ra;
+    pd = sqrt_pos1(xx) * hra;
+    enew = fma(amb, apb, cc * cc) * hra;  // (a^2 + c^2 - b^2) / 2a
+    esub = a - enew;
+}
+
+struct TdState {
+    double X[4], Y[4], Z[4], T[4];  // columns of M_K: images of the x, y, z and E unit vectors; rows x, y, z, E
+    double pd_hi, esub_hi;          // pd[K] and esub[K] of the step above
+    double wn;                      // running product of the two-body momenta
+};
+
+template <class Node, int K, class C>
+__device__ __forceinline__ void td_emit(C& c, double* x, double* y, double* z, double* e, double vx, double vy, double vz,
+                                        double ve) {
+    if constexpr (C::early_store && Node::slot < 0)
+        store_row(c.out_row + Node::template child<K>::slot * c.out_stride, vx, vy, vz, ve);
+    // (dead for early-stored leaves; decaying children are read again by the recursion)
+    x[K] = vx, y[K] = vy, z[K] = vz, e[K] = ve;
+}
+
+template <int K, int AB0, int TOPCOL, int ASC, class C>
+__device__ __forceinline__ void td_angles(C& c, double& cz, double& sz, double& cy, double& sy) {
+    double ty, tu;
+    c.template next_turn_desc<AB0 + 2 * (K - 1) + 1, TOPCOL, ASC>(ty, tu);
+    sincos_turn(ty, tu, sy, cy);
+    cz = c.template next_cos_desc<AB0 + 2 * (K - 1), TOPCOL, ASC>();
+    sz = sqrt_unit1(fma(-cz, cz, 1.0));
+}
+
+// step K, N-2 >= K >= 2.  FIRST: the matrix still has the structure R_{N-1} left it with (T = e_E, no E row elsewhere).
+template <class Node, int N, int K, int AB0, int TOPCOL, int ASC, bool FIRST, class C>
+__device__ __forceinline__ void td_step(C& c, TdState& s, const double* inv, const double* m, double* x, double* y,
+                                        double* z, double* e) {
+    double pd, ra, enew, esub;
+    two_body(inv[K], inv[K - 1], m[K], pd, ra, enew, esub);
+    const double g = s.esub_hi * ra, gb = s.pd_hi * ra;  // boost of subsystem K into the rest frame of K+1
+    double cz, sz, cy, sy;
+    td_angles<K, AB0, TOPCOL, ASC>(c, cz, sz, cy, sy);
+    if constexpr (FIRST) {
+        // M B: Y <- g Y + gb T, T <- gb Y + g T with T = (0,0,0,1), Y[3] = 0
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double y0 = s.Y[r];
+            s.Y[r] = g * y0;
+            s.T[r] = gb * y0;
+        }
+        s.Y[3] = gb;
+        s.T[3] = g;
+        // M Ry: X <- cy X + sy Z, Z <- cy Z - sy X with X[3] = Z[3] = Z[1] = 0
+#pragma unroll
+        for (int r = 0; r < 3; r += 2) {
+            const double x0 = s.X[r], z0 = s.Z[r];
+            s.X[r] = fma(cy, x0, sy * z0);
+            s.Z[r] = fma(cy, z0, -(sy * x0));
+        }
+        {
+            const double x0 = s.X[1];
+            s.X[1] = cy * x0;
+            s.Z[1] = -(sy * x0);
+        }
+        // M Rz: X <- cz X + sz Y, Y <- cz Y - sz X with X[3] = 0
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double x0 = s.X[r], y0 = s.Y[r];
+            s.X[r] = fma(cz, x0, sz * y0);
+            s.Y[r] = fma(cz, y0, -(sz * x0));
+        }
+        s.X[3] = sz * gb;
+        s.Y[3] = cz * gb;
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double y0 = s.Y[r], t0 = s.T[r];
+            s.Y[r] = fma(g, y0, gb * t0);
+            s.T[r] = fma(g, t0, gb * y0);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double x0 = s.X[r], z0 = s.Z[r];
+            s.X[r] = fma(cy, x0, sy * z0);
+            s.Z[r] = fma(cy, z0, -(sy * x0));
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double x0 = s.X[r], y0 = s.Y[r];
+            s.X[r] = fma(cz, x0, sz * y0);
+            s.Y[r] = fma(cz, y0, -(sz * x0));
+        }
+    }
+    // p_K = M_K (0, -pd, 0, enew)
+    td_emit<Node, K>(c, x, y, z, e, fma(enew, s.T[0], -(pd * s.Y[0])), fma(enew, s.T[1], -(pd * s.Y[1])),
+                     fma(enew, s.T[2], -(pd * s.Y[2])), fma(enew, s.T[3], -(pd * s.Y[3])));
+    s.pd_hi = pd;
+    s.esub_hi = esub;
+    s.wn = s.wn * pd;
+}
+
+template <class Node, int N, int AB0, int TOPCOL, int ASC, class C, int... I>
+__device__ __forceinline__ void td_steps(C& c, TdState& s, const double* inv, const double* m, double* x, double* y,
+                                         double* z, double* e, Seq<I...>) {
+    // I = 0 .. N-4  ->  K = N-2 .. 2
+    (td_step<Node, N, N - 2 - I, AB0, TOPCOL, ASC, I == 0>(c, s, inv, m, x, y, z, e), ...);
+}
+
+// Returns the product of the two-body momenta of the node; the children's 4-vectors in the node's rest frame go to
+// x, y, z, e (or, for a top particle at rest in a generating kernel, straight to the output planes).
+template <class Node, int N, int AB0, int ASC, class C>
+__device__ __forceinline__ double genbod_topdown(C& c, const double* inv, const double* m, double* x, double* y, double* z,
+                                                 double* e) {
+    static_assert(N >= 4, "the top-down path needs at least one middle step");
+    constexpr int TOPCOL = AB0 + 2 * (N - 2) + 1;
+    TdState s;
+    {  // K = N-1: M = R_{N-1}
+        constexpr int K = N - 1;
+        double pd, ra, enew, esub;
+        two_body(inv[K], inv[K - 1], m[K], pd, ra, enew, esub);
+        double cz, sz, cy, sy;
+        td_angles<K, AB0, TOPCOL, ASC>(c, cz, sz, cy, sy);
+        const double t = sz * pd;
+        td_emit<Node, K>(c, x, y, z, e, cy * t, -(cz * pd), sy * t, enew);
+        s.X[0] = cy * cz, s.X[1] = sz, s.X[2] = sy * cz, s.X[3] = 0.0;
+        s.Y[0] = -(cy * sz), s.Y[1] = cz, s.Y[2] = -(sy * sz), s.Y[3] = 0.0;
+        s.Z[0] = -sy, s.Z[1] = 0.0, s.Z[2] = cy, s.Z[3] = 0.0;
+        s.T[0] = s.T[1] = s.T[2] = 0.0, s.T[3] = 1.0;
+        s.pd_hi = pd, s.esub_hi = esub, s.wn = pd;
+    }
+    td_steps<Node, N, AB0, TOPCOL, ASC>(c, s, inv, m, x, y, z, e, MakeSeq<N - 3>{});
+    {  // K = 1: only the y and E columns of M_1 are needed, for particles 1 and 0 (back to back)
+        double pd, ra, enew, esub;
+        two_body(inv[1], inv[0], m[1], pd, ra, enew, esub);
+        const double g = s.esub_hi * ra, gb = s.pd_hi * ra;
+        double cz, sz, cy, sy;
+        td_angles<1, AB0, TOPCOL, ASC>(c, cz, sz, cy, sy);
+        double v1[4], v0[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double y0 = s.Y[r], t0 = s.T[r];
+            const double yb = fma(g, y0, gb * t0), tb = fma(g, t0, gb * y0);  // M B
+            const double xr = fma(cy, s.X[r], sy * s.Z[r]);                    // x column of M B Ry
+            const double yr = fma(cz, yb, -(sz * xr));                          // y column of M_1
+            const double a = pd * yr;
+            v1[r] = fma(enew, tb, -a);  // M_1 (0, -pd, 0, enew[1])
+            v0[r] = fma(esub, tb, a);   // M_1 (0, +pd, 0, esub[0])
+        }
+        td_emit<Node, 1>(c, x, y, z, e, v1[0], v1[1], v1[2], v1[3]);
+        td_emit<Node, 0>(c, x, y, z, e, v0[0], v0[1], v0[2], v0[3]);
+        s.wn = s.wn * pd;
+    }
+    return s.wn;
+}
+
 template <class Node, class C, int... J>
 __device__ __forceinline__ void store_children(C& c, const double* m, const double* x, const double* y, const double* z,
                                                const double* e, Seq<J...>) {
@@ -539,22 +792,28 @@ __device__ __forceinline__ double gen_node(C& c, const PsParams& prm, long long 
 #pragma unroll
         for (int j = 0; j < N; ++j) x[j] = y[j] = z[j] = e[j] = 0.0;
     } else {
-        double pd[N - 1], ra[N - 1], enew[N], esub[N - 1];
+        if constexpr (N >= PS_TOPDOWN_MIN_N) {
+            // block index the ascending draws (sampled children, sorted uniforms) stopped in: still held in c.w
+            constexpr int ASC = AB0 > 0 ? (PS_UNIFORM_BITS * AB0 - 1) / 128 : -1;
+            wn = genbod_topdown<Node, N, AB0, ASC>(c, inv, m, x, y, z, e);
+        } else {
+            double pd[N - 1], ra[N - 1], enew[N], esub[N - 1];
 #pragma unroll
-        for (int j = 0; j < N - 1; ++j) {
-            const double a = inv[j + 1], b = inv[j], cc = m[j + 1];
-            const double amb = a - b, apb = a + b;
-            const double xx = (amb - cc) * (apb + cc) * (amb + cc) * (apb - cc);
-            ra[j] = rcp_pos1(a);
-            const double hra = 0.5 * ra[j];
-            pd[j] = sqrt_pos1(xx) * hra;
-            enew[j + 1] = fma(amb, apb, cc * cc) * hra;  // (a^2 + c^2 - b^2) / 2a
-            esub[j] = a - enew[j + 1];
+            for (int j = 0; j < N - 1; ++j) {
+                const double a = inv[j + 1], b = inv[j], cc = m[j + 1];
+                const double amb = a - b, apb = a + b;
+                const double xx = (amb - cc) * (apb + cc) * (amb + cc) * (apb - cc);
+                ra[j] = rcp_pos1(a);
+                const double hra = 0.5 * ra[j];
+                pd[j] = sqrt_pos1(xx) * hra;
+                enew[j + 1] = fma(amb, apb, cc * cc) * hra;  // (a^2 + c^2 - b^2) / 2a
+                esub[j] = a - enew[j + 1];
+            }
+            wn = pd[0];
+#pragma unroll
+            for (int j = 1; j < N - 1; ++j) wn = wn * pd[j];
+            genbod_steps_fast<N, AB0>(c, pd, ra, enew, esub, x, y, z, e, MakeSeq<N - 1>{});
         }
-        wn = pd[0];
-#pragma unroll
-        for (int j = 1; j < N - 1; ++j) wn = wn * pd[j];
-        genbod_steps_fast<N, AB0>(c, pd, ra, enew, esub, x, y, z, e, MakeSeq<N - 1>{});
         if constexpr (!REST) {
             // boost by the parent: u = gamma*beta = p/M, gamma = E/M;  p' = p + (u.p/(gamma+1) + E) u ; E' = gamma E + u.p
             const double rM = rcp_pos1(M);
@@ -686,35 +945,11 @@ __device__ __forceinline__ void event_w_max(const C& c, const PsParams& prm, dou
     }
 }
 
-// ------------------------------------------------------------------ stores
-// One 256-bit store per particle per thread: a warp writes 32 consecutive 32-byte rows = 1 KiB
-// contiguous, i.e. eight full 128-byte lines per instruction (STG.E.ENL2.256 on sm_100a; PTX ISA 8.8,
-// CUDA >= 12.9).  Older NVRTC versions (PTX 8.7) fall back to two 128-bit halves.
-#if defined(__CUDACC_VER_MAJOR__) && (__CUDACC_VER_MAJOR__ * 100 + __CUDACC_VER_MINOR__ >= 1209)
-#define PS_HAVE_V4F64 1
-#else
-#define PS_HAVE_V4F64 0
-#endif
-__device__ __forceinline__ void store_row(double* p, double a, double b, double c, double d) {
-#if PS_HAVE_V4F64
-    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-#else
-    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
-    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p + 2), "d"(c), "d"(d) : "memory");
-#endif
-}
-__device__ __forceinline__ void load_row(const double* p, double& a, double& b, double& c, double& d) {
-#if PS_HAVE_V4F64
-    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-#else
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(d) : "l"(p + 2));
-#endif
-}
-
-template <class C, int... S>
+// ------------------------------------------------------------------ stores (store_row / load_row: see above the top-down path)
+// slots below FIRST were stored early (Ctx::early_store)
+template <int FIRST, class C, int... S>
 __device__ __forceinline__ void store_particles(const C& c, double* base, long long stride, Seq<S...>) {
-    (store_row(base + S * stride, c.px[S], c.py[S], c.pz[S], c.en[S]), ...);
+    ((S >= FIRST ? store_row(base + S * stride, c.px[S], c.py[S], c.pz[S], c.en[S]) : (void)0), ...);
 }
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -770,12 +1005,16 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
         {
         const long long i = tile * PS_BLOCK + threadIdx.x;
         if (i < n) {
-            Ctx<P, DBG, false, use_keyed_philox<Tree>()> c;
+            // the children of a top particle at rest come out of the top-down path final: stored as they are formed
+            constexpr bool EARLY = !BOOST && !PS_EXACT && Tree::nch >= PS_TOPDOWN_MIN_N;
+            Ctx<P, DBG, false, use_keyed_philox<Tree>(), EARLY> c;
             c.seed = prm.seed;
             c.keys = prm.philox_keys;
             c.event = prm.event_index ? (unsigned long long)prm.event_index[i] : prm.first_event + (unsigned long long)i;
             c.dbg_row = DBG ? prm.dbg_u + i * prm.dbg_ncols : nullptr;
             c.bad = false;
+            c.out_row = prm.particles + i * 4;
+            c.out_stride = prm.particle_stride;
             double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
             if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
             const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
@@ -792,7 +1031,7 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
                 prm.weights_max[i] = w_max;
             }
             prm.weights[i] = w_out;
-            store_particles(c, prm.particles + i * 4, prm.particle_stride, MakeSeq<P>{});
+            store_particles<EARLY ? Tree::nch : 0>(c, prm.particles + i * 4, prm.particle_stride, MakeSeq<P>{});
             bad_any |= c.bad;
             st_max = w_out > st_max ? w_out : st_max;  // (fmax / fmin: seven instructions each on sm_100a, see cmp_exchange)
             st_sum += w_out;
@@ -905,8 +1144,13 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
     if (bad_any) *prm.err_flag = PS_ERR_FORBIDDEN;
 }
 
+// The weights-only pass holds no 4-vectors: at three resident CTAs (<= 80 registers, no spills) the ten-body mask pass
+// takes 2.81 instead of 2.97 ms per 2^27 candidates on a B200 (four CTAs, 62 registers: 2.88 ms).
+#ifndef PS_MASK_MIN_BLOCKS
+#define PS_MASK_MIN_BLOCKS 3
+#endif
 template <class Tree, bool BOOST, int EXACT>
-__global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS)
+__global__ void __launch_bounds__(PS_BLOCK, PS_MASK_MIN_BLOCKS)
     genbod_mask_kernel(const __grid_constant__ PsParams prm, double w_bound, unsigned int* mask,
                        unsigned long long* overflow) {
     static_assert(EXACT == PS_EXACT, "variant tag must match the translation unit");

@@ -82,6 +82,11 @@ def _structure(part):
     return (id(part), tuple(_structure(c) for c in part.children))
 
 
+# Bumped by every set_children anywhere: a compiled tree is re-validated (by its structure) only when some tree in the
+# process has changed since it was compiled -- not on every generate() call.
+_TREE_EPOCH = 0
+
+
 def process_list_to_tensor(lst, device=None):
     """ps.py:37-53 -- a Python *list* is transposed (read as ``(4, N)``), anything else is taken as is."""
     if isinstance(lst, list):
@@ -92,7 +97,8 @@ def process_list_to_tensor(lst, device=None):
 
 
 def _ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    """Device (or host) address for a ``c_void_p`` argument: ctypes converts a plain int itself."""
+    return t.data_ptr() if t is not None else None
 
 
 class CompiledDecay:
@@ -143,6 +149,7 @@ class CompiledDecay:
         self.has_resonances = any(d[1] != _lib.PS_MASS_FIXED for d in descs)
         self.top_is_resonance = not top.has_fixed_mass
         self.structure = _structure(top)
+        self.epoch = _TREE_EPOCH
         self._err_flags = {}
         self._static_forbidden = self._check_static()
 
@@ -205,24 +212,29 @@ class CompiledDecay:
 
     # ------------------------------------------------------------------ the one C-ABI call
     def launch(self, n_events: int, seed: int, first_event: int = 0, boost_to=None, normalize_weights=True,
-               exact=False, debug_uniforms=None, user_masses=None, out=None, stats=None, err=None, stream=None):
+               exact=False, debug_uniforms=None, user_masses=None, out=None, stats=None, err=None, stream=None,
+               _device_hint=None):
         """Generate events ``[first_event, first_event + n_events)`` of stream ``seed`` on the current device.
 
         ``out`` may hold preallocated ``weights`` ``(N,)``, ``particles`` ``(P, N, 4)`` and
         ``weights_max`` ``(N,)`` tensors to reuse.  Returns ``(weights, weights_max | None, particles, err)``.
         """
-        device = _device()
+        device = _device_hint or _device()
         n = int(n_events)
         if self.top_is_resonance and boost_to is None:
             raise ValueError("Cannot use resonance as top particle")  # ps.py:543
-        out = out or {}
-        weights, particles = out.get("weights"), out.get("particles")
-        weights_max = out.get("weights_max") if not normalize_weights else None
-        _check_out(weights, "weights", (n,), device)
-        _check_out(particles, "particles", (self.n_particles, n, 4), device, planes=True)
-        _check_out(weights_max, "weights_max", (n,), device)
-        _check_out(stats, "stats", (4,), device)
-        _check_out(err, "err", (1,), device, dtype=torch.int32)
+        if out:
+            weights, particles = out.get("weights"), out.get("particles")
+            weights_max = out.get("weights_max") if not normalize_weights else None
+            _check_out(weights, "weights", (n,), device)
+            _check_out(particles, "particles", (self.n_particles, n, 4), device, planes=True)
+            _check_out(weights_max, "weights_max", (n,), device)
+        else:
+            weights = particles = weights_max = None
+        if stats is not None:
+            _check_out(stats, "stats", (4,), device)
+        if err is not None:
+            _check_out(err, "err", (1,), device, dtype=torch.int32)
         if weights is None and particles is None and weights_max is None:
             # one allocation for everything: [particles (P,n,4) | weights (n) | weights_max (n)]
             extra = 1 if normalize_weights else 2
@@ -257,7 +269,7 @@ class CompiledDecay:
         rc = _lib.lib.ps_generate(
             self.handle, int(seed) & (2**64 - 1), int(first_event), n, _ptr(boost_to), boost_rows,
             _ptr(debug_uniforms), _ptr(user_masses), _ptr(weights), _ptr(weights_max), _ptr(particles),
-            int(stride), _ptr(stats), _ptr(err), flags, ctypes.c_void_p(stream),
+            int(stride), _ptr(stats), _ptr(err), flags, stream,
         )
         _lib.check(rc)
         return weights, weights_max, particles, err
@@ -345,6 +357,8 @@ class GenParticle:
         if name_clash := self._do_names_clash(children):
             raise KeyError(f"Particle name {name_clash} already used")
         self.children = children
+        global _TREE_EPOCH
+        _TREE_EPOCH += 1
         return self
 
     @property
@@ -369,13 +383,18 @@ class GenParticle:
     def compile(self) -> CompiledDecay:
         """Compile (once) the decay tree below this particle into its kernel descriptor."""
         # a leaf can still get children after this tree was compiled (ps.py:207-210 latches decaying particles only)
-        if self._compiled is None or self._compiled.structure != _structure(self):
-            def fused(part):
-                return all(
-                    (c.has_fixed_mass or hasattr(c._mass, "_ps_sampler")) and fused(c) for c in part.children
-                )
+        compiled = self._compiled
+        if compiled is not None:
+            if compiled.epoch == _TREE_EPOCH:
+                return compiled
+            if compiled.structure == _structure(self):
+                compiled.epoch = _TREE_EPOCH
+                return compiled
 
-            self._compiled = CompiledDecay(self, split=not fused(self))
+        def fused(part):
+            return all((c.has_fixed_mass or hasattr(c._mass, "_ps_sampler")) and fused(c) for c in part.children)
+
+        self._compiled = CompiledDecay(self, split=not fused(self))
         return self._compiled
 
     # ------------------------------------------------------------------ generation
@@ -387,7 +406,7 @@ class GenParticle:
         seed: SeedLike = None,
         *,
         as_vectors: bool | None = None,
-        exact: bool = False,
+        exact: bool | None = None,
         debug_uniforms=None,
         _deferred_checks: list | None = None,
     ):
@@ -403,7 +422,10 @@ class GenParticle:
             normalize_weights: divide the weights by their analytic maximum.
             seed: ``None`` (global generator), an int, or a ``phasespace_b200.random.Generator``.
             as_vectors: return ``vector`` objects instead of tensors (needs the ``vector`` package).
-            exact: (extension) run the variant that keeps the reference's operation order.
+            exact: (extension) run the variant that keeps the reference's operation order, op for op, including its
+                re-derivation of every decaying particle's mass from its boosted 4-vector (ps.py:322); ``False``: the
+                product kernel (same function of the draws, restructured arithmetic).  Default: ``True`` in debug
+                mode (``debug_uniforms`` given), else ``False``.
             debug_uniforms: (extension) ``(n_events, n_draws)`` uniforms in the reference's draw order,
                 used instead of the in-kernel RNG -- the parity/debug mode.
 
@@ -436,6 +458,8 @@ class GenParticle:
                     f"of {tuple(boost_to.shape)}"
                 )
             boost_to = boost_to.contiguous()
+        if exact is None:
+            exact = debug_uniforms is not None
         self._mark_generate_called()
         compiled = self.compile()
         if compiled._static_forbidden is not None and boost_to is None:
@@ -451,7 +475,7 @@ class GenParticle:
         first_event = rng.reserve(n_events)
         weights, weights_max, slab, err = compiled.launch(
             n_events, rng.seed, first_event, boost_to=boost_to, normalize_weights=normalize_weights, exact=exact,
-            debug_uniforms=debug_uniforms, user_masses=user_masses,
+            debug_uniforms=debug_uniforms, user_masses=user_masses, _device_hint=device,
         )
         if (compiled.has_resonances or boost_to is not None) and n_events > 0:
             if _deferred_checks is not None:  # GenMultiDecay checks all modes with one synchronisation

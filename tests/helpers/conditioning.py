@@ -26,7 +26,7 @@ energy -- instead of allowing a blanket fraction of events a blanket looser tole
 import numpy as np
 
 EPS = 2.0 ** -53
-MASS_NOISE = 1e-13  # relative agreement of in-kernel sampled resonance masses with the oracle's
+MASS_NOISE = 2e-13  # relative agreement of in-kernel sampled resonance masses with the oracle's
 
 
 def _mass(v):
