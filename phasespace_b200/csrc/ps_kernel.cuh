@@ -982,8 +982,16 @@ __host__ __device__ constexpr bool use_keyed_philox() {
     return Tree::n_draws > PS_KEYED_MIN_DRAWS;
 }
 
-template <class Tree, bool BOOST, bool DBG>
-__device__ __forceinline__ void genbod_body(const PsParams& prm) {
+// PLAIN: the call every user makes -- consecutive event indices, normalised weights (no event_index list, no weights_max
+// output): the three run-time questions about them leave the loop.  STATS: weight statistics requested (prm.stats).
+// A kernel holds the plain body with and without statistics and the general one (genbod_dispatch); per event the plain
+// body without statistics is 23 instructions shorter for three bodies (322 instead of 345), which is what counts once the
+// board sits at its power limit and the kernel is bound by issue slots rather than by HBM.
+#ifndef PS_SPECIALIZE
+#define PS_SPECIALIZE 1
+#endif
+template <class Tree, bool BOOST, bool DBG, bool PLAIN, bool STATS>
+__device__ __forceinline__ void genbod_body_impl(const PsParams& prm) {
     constexpr int P = Tree::n_below;
     static_assert(P <= PS_MAX_SLOTS, "decay tree too large");
 
@@ -1010,7 +1018,10 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
             Ctx<P, DBG, false, use_keyed_philox<Tree>(), EARLY> c;
             c.seed = prm.seed;
             c.keys = prm.philox_keys;
-            c.event = prm.event_index ? (unsigned long long)prm.event_index[i] : prm.first_event + (unsigned long long)i;
+            if constexpr (PLAIN)
+                c.event = prm.first_event + (unsigned long long)i;
+            else
+                c.event = prm.event_index ? (unsigned long long)prm.event_index[i] : prm.first_event + (unsigned long long)i;
             c.dbg_row = DBG ? prm.dbg_u + i * prm.dbg_ncols : nullptr;
             c.bad = false;
             c.out_row = prm.particles + i * 4;
@@ -1019,9 +1030,9 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
             if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
             const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
             double w_max, inv_w_max;
-            event_w_max<Tree, BOOST>(c, prm, bx, by, bz, be, !prm.normalize && prm.weights_max, w_max, inv_w_max);
+            event_w_max<Tree, BOOST>(c, prm, bx, by, bz, be, !PLAIN && !prm.normalize && prm.weights_max, w_max, inv_w_max);
             double w_out = w;
-            if (prm.normalize) {  // phasespace.py:713-717
+            if (PLAIN || prm.normalize) {  // phasespace.py:713-717
 #if PS_EXACT
                 w_out = w / w_max;
 #else
@@ -1033,19 +1044,21 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
             prm.weights[i] = w_out;
             store_particles<EARLY ? Tree::nch : 0>(c, prm.particles + i * 4, prm.particle_stride, MakeSeq<P>{});
             bad_any |= c.bad;
-            st_max = w_out > st_max ? w_out : st_max;  // (fmax / fmin: seven instructions each on sm_100a, see cmp_exchange)
-            st_sum += w_out;
-            st_sum2 += w_out * w_out;
+            if constexpr (STATS) {
+                st_max = w_out > st_max ? w_out : st_max;  // (fmax / fmin: seven instructions each on sm_100a, see cmp_exchange)
+                st_sum += w_out;
+                st_sum2 += w_out * w_out;
 #if PS_EXACT
-            st_wmax = w_max > st_wmax ? w_max : st_wmax;
+                st_wmax = w_max > st_wmax ? w_max : st_wmax;
 #else
-            st_inv_min = inv_w_max < st_inv_min ? inv_w_max : st_inv_min;  // max w_max = 1 / min (1 / w_max)
+                st_inv_min = inv_w_max < st_inv_min ? inv_w_max : st_inv_min;  // max w_max = 1 / min (1 / w_max)
 #endif
+            }
         }
         }
     }
     if (bad_any) *prm.err_flag = PS_ERR_FORBIDDEN;
-    if (prm.stats) {  // epilogue: warp shuffle -> shared -> one atomic per CTA
+    if (STATS && prm.stats) {  // epilogue: warp shuffle -> shared -> one atomic per CTA
         __shared__ double red[4][PS_BLOCK / 32];
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         st_max = warp_max(st_max);
@@ -1080,6 +1093,22 @@ __device__ __forceinline__ void genbod_body(const PsParams& prm) {
             }
         }
     }
+}
+
+template <class Tree, bool BOOST, bool DBG>
+__device__ __forceinline__ void genbod_body(const PsParams& prm) {
+#if PS_SPECIALIZE
+    if constexpr (!DBG) {  // the debug kernels are for parity, not for speed: one body
+        if (!prm.event_index && prm.normalize) {
+            if (prm.stats)
+                genbod_body_impl<Tree, BOOST, DBG, true, true>(prm);
+            else
+                genbod_body_impl<Tree, BOOST, DBG, true, false>(prm);
+            return;
+        }
+    }
+#endif
+    genbod_body_impl<Tree, BOOST, DBG, false, true>(prm);
 }
 
 // EXACT only distinguishes the symbol names of the two arithmetic variants (it must equal PS_EXACT).

@@ -9,14 +9,15 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 CONFIGS = ["flat 2-body", "flat 3-body (headline)", "flat 4-body", "flat 6-body", "flat 10-body",
            "flat 4-body + per-event boost_to", "K* gamma chain, fixed K*", "K* gamma chain, Cauchy K*",
            "K* gamma chain, truncated-normal K*", "K* gamma chain, relativistic BW K*",
+           "10-body weights-only mask pass of the unweighting (config 5)",
            "3-body fused histograms (13 x 100 bins; native 32-bit shared atomics on fixed-point limbs)"]
 KEYS = ["flat_2body", "flat_3body", "flat_4body", "flat_6body", "flat_10body", "flat_4body_boost", "kstar_gamma_fixed",
-        "kstar_gamma_bw", "kstar_gamma_gauss", "kstar_gamma_relbw", None]
+        "kstar_gamma_bw", "kstar_gamma_gauss", "kstar_gamma_relbw", "mask_10body", None]
 rows = list(csv.DictReader(l for l in open(src) if l.startswith('"')))
 launches = {}
 for r in rows:
     launches.setdefault(int(r["ID"]), {"kernel": r["Kernel Name"]})[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
-# generate_histograms() runs a small pilot generation before its fused kernel: keep the ten generator launches and
+# generate_histograms() runs a small pilot generation before its fused kernel: keep the ten generator launches, the mask pass and
 # the histogram kernel (the last launch)
 ordered = [m for _, m in sorted(launches.items())]
 ordered = ordered[:len(CONFIGS) - 1] + [ordered[-1]]

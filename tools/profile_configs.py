@@ -37,6 +37,16 @@ for fac in (None, mf.breitwigner_factory, mf.gauss_factory, mf.relativistic_brei
     kst = ps.GenParticle("K*0", 895.81 if fac is None else fac(895.81, 47.4))
     once(ps.GenParticle("B0", B0).set_children(kst.set_children(ps.GenParticle("K+", K), ps.GenParticle("pi-", PI)),
                                                ps.GenParticle("gamma", 0.0)))
+# the weights-only pass of the accept-reject unweighting (BASELINE config 5), ten bodies
+import ctypes
+from phasespace_b200 import _lib
+from phasespace_b200.phasespace import _ptr
+ten = ps.nbody_decay(B0, [PI] * 10).compile()
+mask = torch.empty(((n + 31) // 32,), dtype=torch.int32, device=dev)
+state = torch.zeros((2,), dtype=torch.int64, device=dev)
+_lib.check(_lib.lib.ps_unweight_mask(ten.handle, 1, 0, n, 1e-6, _ptr(mask), _ptr(state[:1]), _ptr(state[1:].view(torch.int32)[:1]), 0,
+                                     ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+torch.cuda.synchronize()
 generate_histograms(ps.nbody_decay(B0, [PI] * 3), n, seed=1)
 torch.cuda.synchronize()
 print("done")
