@@ -66,6 +66,7 @@ struct Pt {
     static constexpr bool sampled = (KIND == PS_KIND_GAUSS || KIND == PS_KIND_BW || KIND == PS_KIND_RELBW);
     static constexpr int n_below = (0 + ... + (1 + Ch::n_below));
     static constexpr int n_sampled_children = (0 + ... + (Ch::sampled ? 1 : 0));
+    static constexpr int n_sampled_below = (0 + ... + ((Ch::sampled ? 1 : 0) + Ch::n_sampled_below));
     // uniform draws of this node and of everything below it (ps_tree_n_draws): 3n-4 per decay + one per sampled child
     static constexpr int n_draws =
         (sizeof...(Ch) == 0 ? 0 : (int)(3 * sizeof...(Ch)) - 4 + n_sampled_children) + (0 + ... + Ch::n_draws);
@@ -123,10 +124,13 @@ struct WmaxAcc {
 // registers, a different store schedule), so the small trees keep the seed form (use_keyed_philox).
 // EARLY: the children of a top particle that decays at rest through the top-down path (genbod_topdown) are final as soon
 // as they are formed and are stored right away (out_row / out_stride) instead of being held until the end of the event.
-template <int P, bool DBG, bool WONLY = false, bool KEYED = true, bool EARLY = false>
+// TABLE: the azimuths use the table-driven sincos (ps_fastmath.cuh sincos_turn, use_turn_table below).
+template <int P, bool DBG, bool WONLY = false, bool KEYED = true, bool EARLY = false, bool TABLE = false>
 struct Ctx {
     static constexpr bool wonly = WONLY && !PS_EXACT;
     static constexpr bool early_store = EARLY && !PS_EXACT;
+    static constexpr bool turn_table = TABLE;
+    static constexpr double turn_s = turn_scale<TABLE>();
     double px[P], py[P], pz[P], en[P], ms[P];
     double* out_row;        // EARLY: row of this event in particle plane 0
     long long out_stride;   // EARLY: doubles between planes
@@ -198,15 +202,15 @@ struct Ctx {
             return fma(mantissa_desc<COL, TOPCOL, ASC>(), 4.0, -5.0);
     }
     template <int COL, int TOPCOL, int ASC>
-    __device__ __forceinline__ void next_turn_desc(double& y, double& u2) {
+    __device__ __forceinline__ void next_turn_desc(double& y, double& t) {
         if constexpr (DBG) {
             const double u = dbg_row[COL];
-            y = fma(u, 4.0, PS_TURN_MAGIC);
-            u2 = u + u;
+            y = fma(u, turn_s, PS_TURN_MAGIC);
+            t = u * turn_s;
         } else {
             const double d = mantissa_desc<COL, TOPCOL, ASC>();
-            y = fma(d, 8.0, PS_TURN_MAGIC - 8.0);
-            u2 = fma(d, 4.0, -4.0);
+            y = fma(d, 2.0 * turn_s, PS_TURN_MAGIC - 2.0 * turn_s);
+            t = fma(d, 2.0 * turn_s, -2.0 * turn_s);
         }
     }
     // the uniform u = 2 d - 2 itself
@@ -225,18 +229,18 @@ struct Ctx {
         else
             return fma(mantissa<COL>(), 4.0, -5.0);
     }
-    // the arguments of sincos_turn for the azimuth 2 pi u: y = 4 u + PS_TURN_MAGIC (one rounding of the same real number
-    // either way) and 2 u (exact)
+    // the arguments of sincos_turn for the azimuth 2 pi u: y = S u + PS_TURN_MAGIC (one rounding of the same real number
+    // either way) and t = S u (exact: S = turn_scale<TABLE>() is a power of two)
     template <int COL>
-    __device__ __forceinline__ void next_turn(double& y, double& u2) {
+    __device__ __forceinline__ void next_turn(double& y, double& t) {
         if constexpr (DBG) {
             const double u = dbg_row[COL];
-            y = fma(u, 4.0, PS_TURN_MAGIC);
-            u2 = u + u;
+            y = fma(u, turn_s, PS_TURN_MAGIC);
+            t = u * turn_s;
         } else {
             const double d = mantissa<COL>();
-            y = fma(d, 8.0, PS_TURN_MAGIC - 8.0);
-            u2 = fma(d, 4.0, -4.0);
+            y = fma(d, 2.0 * turn_s, PS_TURN_MAGIC - 2.0 * turn_s);
+            t = fma(d, 2.0 * turn_s, -2.0 * turn_s);
         }
     }
 };
@@ -428,7 +432,7 @@ __device__ __forceinline__ void genbod_step_fast(C& c, const double* pd, const d
     const double sz = sqrt_unit1(fma(-cz, cz, 1.0));
     double ty, tu, sy, cy;
     c.template next_turn<AB + 1>(ty, tu);
-    sincos_turn(ty, tu, sy, cy);
+    sincos_turn<C::turn_table>(ty, tu, sy, cy);
     const double t = sz * pd[K - 1];
     if constexpr (K == 1) {
         // particles 0 and 1 are back to back: (0, +-pd0, 0) rotated
@@ -546,7 +550,7 @@ template <int K, int AB0, int TOPCOL, int ASC, class C>
 __device__ __forceinline__ void td_angles(C& c, double& cz, double& sz, double& cy, double& sy) {
     double ty, tu;
     c.template next_turn_desc<AB0 + 2 * (K - 1) + 1, TOPCOL, ASC>(ty, tu);
-    sincos_turn(ty, tu, sy, cy);
+    sincos_turn<C::turn_table>(ty, tu, sy, cy);
     cz = c.template next_cos_desc<AB0 + 2 * (K - 1), TOPCOL, ASC>();
     sz = sqrt_unit1(fma(-cz, cz, 1.0));
 }
@@ -981,6 +985,19 @@ template <class Tree>
 __host__ __device__ constexpr bool use_keyed_philox() {
     return Tree::n_draws > PS_KEYED_MIN_DRAWS;
 }
+// trees that are bound by instruction issue rather than by HBM use the table-driven sincos (ps_fastmath.cuh): more than
+// PS_TABLE_MIN_DRAWS - 1 draws per event, or (PS_TABLE_SAMPLED) a resonance sampled in the kernel (K* gamma with a
+// relativistic Breit-Wigner K*: 3.31 -> 3.22 ms per 1e8 events, Cauchy 2.11 -> 2.05)
+#ifndef PS_TABLE_MIN_DRAWS
+#define PS_TABLE_MIN_DRAWS 6
+#endif
+#ifndef PS_TABLE_SAMPLED
+#define PS_TABLE_SAMPLED 1
+#endif
+template <class Tree>
+__host__ __device__ constexpr bool use_turn_table() {
+    return Tree::n_draws >= PS_TABLE_MIN_DRAWS || (PS_TABLE_SAMPLED && Tree::n_sampled_below > 0);
+}
 
 // PLAIN: the call every user makes -- consecutive event indices, normalised weights (no event_index list, no weights_max
 // output): the three run-time questions about them leave the loop.  STATS: weight statistics requested (prm.stats).
@@ -1015,7 +1032,7 @@ __device__ __forceinline__ void genbod_body_impl(const PsParams& prm) {
         if (i < n) {
             // the children of a top particle at rest come out of the top-down path final: stored as they are formed
             constexpr bool EARLY = !BOOST && !PS_EXACT && Tree::nch >= PS_TOPDOWN_MIN_N;
-            Ctx<P, DBG, false, use_keyed_philox<Tree>(), EARLY> c;
+            Ctx<P, DBG, false, use_keyed_philox<Tree>(), EARLY, use_turn_table<Tree>()> c;
             c.seed = prm.seed;
             c.keys = prm.philox_keys;
             if constexpr (PLAIN)
@@ -1279,7 +1296,7 @@ __device__ __forceinline__ void genbod_hist_body(const PsParams& prm, const PsHi
     for (long long tile = blockIdx.x; tile * PS_BLOCK < n; tile += gridDim.x) {
         const long long i = tile * PS_BLOCK + threadIdx.x;
         if (i < n) {
-            Ctx<P, false, false, use_keyed_philox<Tree>()> c;
+            Ctx<P, false, false, use_keyed_philox<Tree>(), false, use_turn_table<Tree>()> c;
             c.seed = prm.seed;
             c.keys = prm.philox_keys;
             c.event = prm.first_event + (unsigned long long)i;
