@@ -637,10 +637,11 @@ int pick_grid(const ps_tree* t, const void* fn, int boost, int dbg, int exact, l
         while ((tiles + k - 1) / k > 2147483647LL) k <<= 1;
         g = (tiles + k - 1) / k;
     } else {
-        // Three particles (the flat three-body decay): HBM-bound, and not short of warps -- one CTA per SM streams its
-        // stores 2 % faster than two (1.52 against 1.56 ms per 1e8 events on a B200, equal once the board is at its
-        // power limit), while four bodies and more lose 4 % with one.
-        const int resident = t->n_particles <= 3 ? 1 : per_sm;
+        // Three particles at rest (the flat three-body decay): HBM-bound, and not short of warps -- with ONE CTA per SM
+        // (148 x 256 threads) the stores of the whole chip stay closer together in address and stream 6 % faster than
+        // with two: 1.46 against 1.56 ms per 1e8 events on a B200 (7.1 TB/s), 1.74 against 1.85 ms once the board is
+        // at its power limit.  Four bodies and more are issue-bound and lose 3-18 % with one (profiles/r02_ab_resident.log).
+        const int resident = (t->n_particles <= 3 && !boost) ? 1 : per_sm;
         g = (long long)sms * resident;
         if (g > tiles) g = tiles;
     }
