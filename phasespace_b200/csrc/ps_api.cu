@@ -104,6 +104,7 @@ struct ps_tree {
     // not pay for a mutex and a map lookup keyed on a hundred-character string every time
     mutable std::atomic<const void*> kernel_cache[3][2][2][2] = {};
     mutable std::atomic<int> blocks_per_sm_cache[3][2][2][2] = {};
+    mutable std::atomic<unsigned long long> one_cta_ready[2][2] = {};  // [dbg][exact]: devices (bit mask) on which the shared-memory attribute is set (pick_grid)
 };
 
 namespace {
@@ -614,8 +615,12 @@ int get_kernel_slow(const ps_tree* t, int variant, int boost, int dbg, int exact
 // Launch shape (see genbod_body): a persistent grid of SM count x resident CTAs with a static tile stride;
 // for trees with at most PS_CHUNKED_MAX_P particles (memory-bound) a covering grid with up to 16
 // consecutive tiles per CTA.
+// Dynamic shared memory (unused by the kernel) that makes a second CTA of the same kernel not fit on an SM.
+#define PS_ONE_CTA_SMEM (116 * 1024)
+
 int pick_grid(const ps_tree* t, const void* fn, int boost, int dbg, int exact, long long n_events, int* grid,
-              int* tiles_per_cta) {
+              int* tiles_per_cta, size_t* dyn_smem) {
+    *dyn_smem = 0;
     std::atomic<int>& slot = t->blocks_per_sm_cache[PS_VARIANT_GENERATE][boost ? 1 : 0][dbg ? 1 : 0][exact ? 1 : 0];
     int per_sm = slot.load(std::memory_order_relaxed);
     int sms = 0;
@@ -638,11 +643,24 @@ int pick_grid(const ps_tree* t, const void* fn, int boost, int dbg, int exact, l
         g = (tiles + k - 1) / k;
     } else {
         // Three particles at rest (the flat three-body decay): HBM-bound, and not short of warps -- with ONE CTA per SM
-        // (148 x 256 threads) the stores of the whole chip stay closer together in address and stream 6 % faster than
-        // with two: 1.46 against 1.56 ms per 1e8 events on a B200 (7.1 TB/s), 1.74 against 1.85 ms once the board is
-        // at its power limit.  Four bodies and more are issue-bound and lose 3-18 % with one (profiles/r02_ab_resident.log).
-        const int resident = (t->n_particles <= 3 && !boost) ? 1 : per_sm;
-        g = (long long)sms * resident;
+        // (148 x 256 threads) the stores of the whole chip stay closer together in address and stream 2-3 % faster than
+        // with two (same box, same call: 1.52-1.53 against 1.56 ms per 1e8 events in a burst, 1.84 against 1.85 ms at the
+        // power limit).  Four bodies and more are issue-bound and lose 3-18 % with one (profiles/r02_ab_resident.log).
+        // A grid of one CTA per SM is only that if the hardware cannot double them up (it does when a launch meets the
+        // tail of the previous one: 1.69 instead of 1.46 ms), so the launch asks for more than half an SM's shared memory.
+        const bool one = t->n_particles <= 3 && !boost && per_sm > 1;
+        if (one) {
+            std::atomic<unsigned long long>& ready = t->one_cta_ready[dbg ? 1 : 0][exact ? 1 : 0];
+            int dev = 0;
+            PS_CUDA(cudaGetDevice(&dev));
+            const unsigned long long bit = 1ull << (dev & 63);
+            if (dev >= 64 || !(ready.load(std::memory_order_acquire) & bit)) {  // a function attribute is per device
+                PS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_ONE_CTA_SMEM));
+                ready.fetch_or(bit, std::memory_order_release);
+            }
+            *dyn_smem = PS_ONE_CTA_SMEM;
+        }
+        g = (long long)sms * (one ? 1 : per_sm);
         if (g > tiles) g = tiles;
     }
     *grid = (int)(g < 1 ? 1 : g);
@@ -699,10 +717,11 @@ int launch_generate(const ps_tree* t, PsParams& p, uint32_t flags, void* stream)
     int rc = get_kernel(t, PS_VARIANT_GENERATE, boost, dbg, exact, &fn);
     if (rc) return rc;
     int grid = 1;
-    rc = pick_grid(t, fn, boost, dbg, exact, p.n_events, &grid, &p.tiles_per_cta);
+    size_t dyn_smem = 0;
+    rc = pick_grid(t, fn, boost, dbg, exact, p.n_events, &grid, &p.tiles_per_cta, &dyn_smem);
     if (rc) return rc;
     void* args[] = {&p};
-    PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, 0, (cudaStream_t)stream));
+    PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, dyn_smem, (cudaStream_t)stream));
     g_launches.fetch_add(1);
     return 0;
 }
