@@ -486,7 +486,30 @@ def run_b200(args, rank, local_rank, world):
                         "tests/helpers/rapidsim.py:46-51], normalize_weights=True", "events_per_gpu_per_launch": n3,
             "kernel_ms": ms, "events_per_s": ev_s, **bounds(ev_s / world, 8 + 32 * 4 + 32, "flat_4body_boost"), "clocks": clk,
             "note": "136 B written + 32 B read per event"}
-        del boost, o3
+        del o3
+        torch.cuda.empty_cache()
+        if not args.no_e2e:
+            # the same config end to end with HOST buffers: boost_to rows go H2D and the events come back D2H, both
+            # inside the timed region (generate_host: chunked, copies overlapped with generation)
+            n3h = min(n3, 25_000_000)
+            h_boost = torch.empty((n3h, 4), dtype=torch.float64, pin_memory=True)
+            h_boost.copy_(boost[:n3h])
+            h_out = {"weights": torch.empty((n3h,), dtype=torch.float64, pin_memory=True),
+                     "particles": torch.empty((4, n3h, 4), dtype=torch.float64, pin_memory=True)}
+            d3.generate_host(n3h, boost_to=h_boost, seed=args.seed, out=h_out)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                d3.generate_host(n3h, boost_to=h_boost, seed=args.seed, out=h_out)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            configs["3_four_body_boost_1e8"]["e2e_host"] = {
+                "value": world * n3h * 2 / dt, "unit": UNIT, "events_per_gpu_per_step": n3h, "steps": 2,
+                "h2d_bytes_per_step": 32 * n3h, "d2h_bytes_per_step": 136 * n3h,
+                "gbs_all_ranks_both_directions": world * 168 * n3h * 2 / dt / 1e9,
+                "api": "GenParticle.generate_host(n, boost_to=<pinned host rows>) -> ps_generate_host"}
+            del h_boost, h_out
+        del boost
         torch.cuda.empty_cache()
 
         # ---- config 4: B0 -> K*0(-> K pi) gamma, relativistic Breit-Wigner K*0 sampled in the kernel

@@ -163,6 +163,14 @@ def test_boost_to_broadcast(exact):
     _compare(D.flat_desc(3), N, exact=exact, use_rng=False, boost=boost)
 
 
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+def test_ten_body_boost_to(exact):
+    """The top-down path (nine or more children) under boost_to: no early stores, every product boosted at the end."""
+    n = 4000
+    _compare(D.flat_desc(10), n, exact=exact, use_rng=True, boost=_fonll_like_boost(n, D.B0_MASS, seed=9), normalize=False)
+    _compare(D.flat_desc(9), n, exact=exact, use_rng=False, boost=_fonll_like_boost(1, D.B0_MASS, seed=3))
+
+
 def test_sharding_is_bit_identical():
     """Contiguous index ranges generated separately equal the single launch bit for bit."""
     gen = D.to_gen(D.flat_desc(3))
@@ -311,6 +319,10 @@ _EDGE_TREES = {
                 _leaf("c2", 105.66)]),
             _leaf("b2", 0.0)]),
         _leaf("a2", 938.272)]), 2000, 1e-12),
+    # the top-down path (nine or more children) below the top particle: its products are boosted by the parent afterwards
+    "nine_body_subdecay": (("A", 12000.0, "fixed", 0.0, [
+        ("X", 6000.0, "gauss", 100.0, [_leaf(f"x{i}", 139.57) for i in range(9)]), _leaf("g", 0.0), _leaf("h", 938.272)]),
+        2000, 1e-12),
     "one_kev_above_threshold": (D.flat_desc(3, top=3 * D.PION_MASS + 1e-3, masses=[D.PION_MASS] * 3), 2000, 1e-12),
 }
 
