@@ -950,6 +950,14 @@ __device__ __forceinline__ void event_w_max(const C& c, const PsParams& prm, dou
 }
 
 // ------------------------------------------------------------------ stores (store_row / load_row: see above the top-down path)
+// Per-event inputs (the boost_to row, the event index of the regeneration pass) are the only long-latency loads of the
+// loop, and nothing of an event can start before they return: each thread prefetches the input of its NEXT event into L1
+// while it computes the current one.  Config 3 (four bodies + per-event boost_to): 3.58 -> 3.23 ms per 1e8 events.
+#ifndef PS_PREFETCH_BOOST
+#define PS_PREFETCH_BOOST 1
+#endif
+__device__ __forceinline__ void prefetch_row(const double* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // slots below FIRST were stored early (Ctx::early_store)
 template <int FIRST, class C, int... S>
 __device__ __forceinline__ void store_particles(const C& c, double* base, long long stride, Seq<S...>) {
@@ -1035,16 +1043,30 @@ __device__ __forceinline__ void genbod_body_impl(const PsParams& prm) {
             Ctx<P, DBG, false, use_keyed_philox<Tree>(), EARLY, use_turn_table<Tree>()> c;
             c.seed = prm.seed;
             c.keys = prm.philox_keys;
-            if constexpr (PLAIN)
+            if constexpr (PLAIN) {
                 c.event = prm.first_event + (unsigned long long)i;
-            else
-                c.event = prm.event_index ? (unsigned long long)prm.event_index[i] : prm.first_event + (unsigned long long)i;
+            } else if (prm.event_index) {  // the regeneration pass of the unweighting: this thread's next index into L1
+                c.event = (unsigned long long)prm.event_index[i];
+#if PS_PREFETCH_BOOST
+                if (i + tile_step * PS_BLOCK < n) prefetch_row((const double*)(prm.event_index + i + tile_step * PS_BLOCK));
+#endif
+            } else {
+                c.event = prm.first_event + (unsigned long long)i;
+            }
             c.dbg_row = DBG ? prm.dbg_u + i * prm.dbg_ncols : nullptr;
             c.bad = false;
             c.out_row = prm.particles + i * 4;
             c.out_stride = prm.particle_stride;
             double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
-            if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
+            if constexpr (BOOST) {
+                load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
+#if PS_PREFETCH_BOOST
+                // the row of this thread's NEXT event, into L1 while this event is computed: the load above is the only
+                // long-latency instruction of the loop and nothing can start before it returns
+                const long long i_next = i + tile_step * PS_BLOCK;
+                if (i_next < n) prefetch_row(prm.boost_to + i_next * prm.boost_stride);
+#endif
+            }
             const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
             double w_max, inv_w_max;
             event_w_max<Tree, BOOST>(c, prm, bx, by, bz, be, !PLAIN && !prm.normalize && prm.weights_max, w_max, inv_w_max);
@@ -1303,7 +1325,12 @@ __device__ __forceinline__ void genbod_hist_body(const PsParams& prm, const PsHi
             c.dbg_row = nullptr;
             c.bad = false;
             double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
-            if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
+            if constexpr (BOOST) {
+                load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
+#if PS_PREFETCH_BOOST
+                if (i + (long long)gridDim.x * PS_BLOCK < n) prefetch_row(prm.boost_to + (i + (long long)gridDim.x * PS_BLOCK) * prm.boost_stride);
+#endif
+            }
             const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
             double w_max, inv_w_max;
             event_w_max<Tree, BOOST>(c, prm, bx, by, bz, be, false, w_max, inv_w_max);
