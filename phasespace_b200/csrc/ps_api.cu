@@ -636,7 +636,12 @@ int pick_grid(const ps_tree* t, const void* fn, int boost, int dbg, int exact, l
     const long long tiles = (n_events + PS_BLOCK - 1) / PS_BLOCK;
     int k = 0;
     long long g;
-    if (t->n_particles <= PS_CHUNKED_MAX_P || t->two_body_only) {  // must match CHUNKED in genbod_body
+#ifndef PS_CHUNKED_SAMPLED
+#define PS_CHUNKED_SAMPLED 1
+#endif
+    bool sampled = false;
+    for (const ps_node_desc& nd : t->nodes) sampled = sampled || is_sampled(nd.kind);
+    if (t->n_particles <= PS_CHUNKED_MAX_P || (t->two_body_only && (PS_CHUNKED_SAMPLED || !sampled))) {  // = use_covering_grid<Tree>()
         k = 16;
         while (k > 1 && tiles / k < (long long)sms * per_sm * 4) k >>= 1;  // keep several waves of CTAs
         while ((tiles + k - 1) / k > 2147483647LL) k <<= 1;

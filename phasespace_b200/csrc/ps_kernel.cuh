@@ -989,6 +989,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 #ifndef PS_KEYED_MIN_DRAWS
 #define PS_KEYED_MIN_DRAWS 5
 #endif
+// launch shape (see genbod_body): must match pick_grid in ps_api.cu.  (Chains of two-body decays with a sampled resonance
+// were tried on the persistent grid in round 2: K* gamma Cauchy 1.98 -> 2.10 ms, normal and relativistic BW equal.)
+#ifndef PS_CHUNKED_SAMPLED
+#define PS_CHUNKED_SAMPLED 1
+#endif
+template <class Tree>
+__host__ __device__ constexpr bool use_covering_grid() {
+    return Tree::n_below <= PS_CHUNKED_MAX_P || (Tree::two_body_only && (PS_CHUNKED_SAMPLED || Tree::n_sampled_below == 0));
+}
 template <class Tree>
 __host__ __device__ constexpr bool use_keyed_philox() {
     return Tree::n_draws > PS_KEYED_MIN_DRAWS;
@@ -1029,7 +1038,7 @@ __device__ __forceinline__ void genbod_body_impl(const PsParams& prm) {
     bool bad_any = false;
     const long long n = prm.n_events;
     // the shape is a property of the tree (PS_CHUNKED_MAX_P): the host launches accordingly
-    constexpr bool CHUNKED = P <= PS_CHUNKED_MAX_P || Tree::two_body_only;
+    constexpr bool CHUNKED = use_covering_grid<Tree>();
     const long long n_tiles = (n + PS_BLOCK - 1) / PS_BLOCK;
     long long tile = CHUNKED ? (long long)blockIdx.x * prm.tiles_per_cta : (long long)blockIdx.x;
     const long long tile_end = CHUNKED ? (tile + prm.tiles_per_cta < n_tiles ? tile + prm.tiles_per_cta : n_tiles) : n_tiles;
