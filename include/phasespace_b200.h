@@ -91,11 +91,15 @@ int32_t ps_tree_is_aot(const ps_tree* tree, int32_t with_boost, int32_t with_deb
  *                  (n_events,4) rows; particle_stride >= 4*n_events and a multiple of 4; 32-byte aligned
  *   stats          NULL or device double[4], caller-zeroed, accumulated atomically:
  *                  [max w_out, sum w_out, sum w_out^2, max w_max]
- *   err_flag       device int, caller-zeroed; set to 1 on a forbidden decay */
+ *   err_flag       device int, caller-zeroed; set to 1 on a forbidden decay
+ *   weight_scale   1.0, or (with PS_GEN_NORMALIZE and an event-independent w_max only) a factor multiplied into the
+ *                  normalised weights at no cost: GenMultiDecay.generate divides the weights of every decay mode by the
+ *                  largest maximum weight of all modes (genmultidecay.py:192-195) and passes w_max_mode / w_max_all here
+ *                  instead of generating unnormalised weights and making two more passes over them */
 int ps_generate(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events, const double* boost_to,
                 int64_t boost_rows, const double* debug_uniforms, const double* user_masses, double* weights,
                 double* weights_max, double* particles, int64_t particle_stride, double* stats, int32_t* err_flag,
-                uint32_t flags, void* stream);
+                uint32_t flags, void* stream, double weight_scale);
 
 /* As ps_generate but local event i is global event event_index[i] (device int64 array): the second
  * pass of unweighting regenerates exactly the accepted events. */

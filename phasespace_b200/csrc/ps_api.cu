@@ -736,11 +736,19 @@ int launch_generate(const ps_tree* t, PsParams& p, uint32_t flags, void* stream)
 extern "C" int ps_generate(const ps_tree* tree, uint64_t seed, uint64_t first_event, int64_t n_events,
                            const double* boost_to, int64_t boost_rows, const double* debug_uniforms,
                            const double* user_masses, double* weights, double* weights_max, double* particles,
-                           int64_t particle_stride, double* stats, int32_t* err_flag, uint32_t flags, void* stream) {
+                           int64_t particle_stride, double* stats, int32_t* err_flag, uint32_t flags, void* stream,
+                           double weight_scale) {
     PsParams p;
     int rc = fill_params(tree, p, seed, first_event, nullptr, n_events, boost_to, boost_rows, debug_uniforms, user_masses,
                          weights, weights_max, particles, particle_stride, stats, err_flag, flags);
     if (rc) return rc;
+    if (weight_scale != 1.0) {
+        if (!(weight_scale > 0.0) || !std::isfinite(weight_scale)) return fail(PS_E_INVALID, "weight_scale must be a positive finite number");
+        if (!(flags & PS_GEN_NORMALIZE) || boost_to || tree->resonant_leaf)
+            return fail(PS_E_INVALID, "weight_scale needs PS_GEN_NORMALIZE and an event-independent maximum weight (no boost_to, no resonant leaves)");
+        p.inv_wmax_const = tree->base.inv_wmax_const * weight_scale;  // folded into the constant the kernel multiplies by
+        p.wmax_const = tree->base.wmax_const / weight_scale;
+    }
     return launch_generate(tree, p, flags, stream);
 }
 
@@ -843,7 +851,7 @@ extern "C" int ps_generate_host(const ps_tree* tree, uint64_t seed, uint64_t fir
             rows_arg = per_event_boost ? n : 1;
         }
         rc = ps_generate(tree, seed, first_event + (uint64_t)done, n, boost_arg, rows_arg, nullptr, nullptr, d_w,
-                         want_wmax ? d_wmax : nullptr, d_p, 4 * chunk_events, nullptr, arena->d_err, flags, streams[b]);
+                         want_wmax ? d_wmax : nullptr, d_p, 4 * chunk_events, nullptr, arena->d_err, flags, streams[b], 1.0);
         if (rc) break;
         PS_CUDA(cudaMemcpyAsync(host_weights + done, d_w, (size_t)n * 8, cudaMemcpyDeviceToHost, streams[b]));
         if (want_wmax) PS_CUDA(cudaMemcpyAsync(host_weights_max + done, d_wmax, (size_t)n * 8, cudaMemcpyDeviceToHost, streams[b]));

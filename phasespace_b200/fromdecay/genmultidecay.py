@@ -89,17 +89,31 @@ class GenMultiDecay:
         for st in streams:
             st.wait_stream(main)
         checks = []
+        # genmultidecay.py:192-195 divides every mode's weights by the largest maximum weight of all modes.  When every
+        # populated mode has an event-independent maximum weight (particles at rest with fixed-mass leaves: what a
+        # DecayLanguage chain gives) that number is known before anything is generated, and each kernel normalises by
+        # it directly (w / w_max_mode * (w_max_mode / w_max_all)) -- no weights_max arrays, no max and divide passes.
+        mode_w_max = None
+        if normalize_weights and populated and kwargs.get("boost_to") is None and not kwargs.get("exact"):
+            mode_w_max = [gen.compile().w_max for gen, _ in populated]
+            if not all(np.isfinite(w) and w > 0 for w in mode_w_max):
+                mode_w_max = None
+        total_w_max = max(mode_w_max) if mode_w_max else None
         for k, (gen, n) in enumerate(populated):
+            if mode_w_max:
+                call = dict(normalize_weights=True, _weight_scale=mode_w_max[k] / total_w_max)
+            else:
+                call = dict(normalize_weights=False)
             if streams:
                 with torch.cuda.stream(streams[k % n_streams]):
-                    out = gen.generate(n, normalize_weights=False, seed=rng, _deferred_checks=checks, **kwargs)
-                for t in (out[0], out[1], next(iter(out[2].values()))):
+                    out = gen.generate(n, seed=rng, _deferred_checks=checks, **call, **kwargs)
+                for t in (out[0], next(iter(out[-1].values()))):
                     t.record_stream(main)  # the slab was allocated on the side stream and is consumed on `main`
             else:
-                out = gen.generate(n, normalize_weights=False, seed=rng, _deferred_checks=checks, **kwargs)
+                out = gen.generate(n, seed=rng, _deferred_checks=checks, **call, **kwargs)
             weights.append(out[0])
-            max_weights.append(out[1])
-            events.append(out[2])
+            max_weights.append(None if mode_w_max else out[1])
+            events.append(out[-1])
         for st in streams:
             main.wait_stream(st)
         if checks and bool(torch.stack(checks).any().item()):
@@ -107,6 +121,8 @@ class GenMultiDecay:
 
             raise ForbiddenDecayError("Forbidden decay")
         if normalize_weights:
+            if mode_w_max:
+                return weights, events
             total_max = torch.stack([mw.max() for mw in max_weights]).max()  # genmultidecay.py:193
             return [w / total_max for w in weights], events
         return weights, max_weights, events

@@ -213,11 +213,13 @@ class CompiledDecay:
     # ------------------------------------------------------------------ the one C-ABI call
     def launch(self, n_events: int, seed: int, first_event: int = 0, boost_to=None, normalize_weights=True,
                exact=False, debug_uniforms=None, user_masses=None, out=None, stats=None, err=None, stream=None,
-               _device_hint=None):
+               _device_hint=None, weight_scale=1.0):
         """Generate events ``[first_event, first_event + n_events)`` of stream ``seed`` on the current device.
 
         ``out`` may hold preallocated ``weights`` ``(N,)``, ``particles`` ``(P, N, 4)`` and
         ``weights_max`` ``(N,)`` tensors to reuse.  Returns ``(weights, weights_max | None, particles, err)``.
+        ``weight_scale`` (normalised weights of a tree with an event-independent maximum weight only) is multiplied
+        into the weights inside the kernel at no cost.
         """
         device = _device_hint or _device()
         n = int(n_events)
@@ -269,7 +271,7 @@ class CompiledDecay:
         rc = _lib.lib.ps_generate(
             self.handle, int(seed) & (2**64 - 1), int(first_event), n, _ptr(boost_to), boost_rows,
             _ptr(debug_uniforms), _ptr(user_masses), _ptr(weights), _ptr(weights_max), _ptr(particles),
-            int(stride), _ptr(stats), _ptr(err), flags, stream,
+            int(stride), _ptr(stats), _ptr(err), flags, stream, float(weight_scale),
         )
         _lib.check(rc)
         return weights, weights_max, particles, err
@@ -409,6 +411,7 @@ class GenParticle:
         exact: bool | None = None,
         debug_uniforms=None,
         _deferred_checks: list | None = None,
+        _weight_scale: float = 1.0,
     ):
         """Generate normalized n-body phase space (reference: ps.py:628-717).
 
@@ -475,7 +478,7 @@ class GenParticle:
         first_event = rng.reserve(n_events)
         weights, weights_max, slab, err = compiled.launch(
             n_events, rng.seed, first_event, boost_to=boost_to, normalize_weights=normalize_weights, exact=exact,
-            debug_uniforms=debug_uniforms, user_masses=user_masses, _device_hint=device,
+            debug_uniforms=debug_uniforms, user_masses=user_masses, _device_hint=device, weight_scale=_weight_scale,
         )
         if (compiled.has_resonances or boost_to is not None) and n_events > 0:
             if _deferred_checks is not None:  # GenMultiDecay checks all modes with one synchronisation

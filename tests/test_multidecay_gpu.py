@@ -71,3 +71,44 @@ def test_list_container_and_global_max():
     assert list(events[1]) == ["K*0", "gamma", "K+", "pi-"]
     again, _ = multi.generate(n, normalize_weights=True, seed=3)
     assert all(torch.equal(a, b) for a, b in zip(normed, again))
+
+
+def test_global_max_with_event_dependent_maximum_weights():
+    """A mode whose maximum weight depends on the event (a resonant LEAF, or boost_to) cannot be normalised inside
+    the kernel by a number known in advance: the reference's two-pass recipe (genmultidecay.py:185-195) runs, and the
+    results still equal w / max over all modes of max(w_max)."""
+    from phasespace_b200 import GenParticle
+    from phasespace_b200.fromdecay import mass_functions as mf
+
+    leafy = GenParticle("B0", D.B0_MASS).set_children(
+        GenParticle("rho", mf.breitwigner_factory(775.26, 149.1)), GenParticle("pi", D.PION_MASS), GenParticle("K", D.KAON_MASS))
+    multi = GenMultiDecay([(0.5, phasespace.nbody_decay(D.B0_MASS, [D.PION_MASS] * 4)), (0.5, leafy)])
+    n = 40_000
+    weights, max_weights, events = multi.generate(n, normalize_weights=False, seed=11)
+    assert float(max_weights[1].std()) > 0.0  # really event dependent
+    normed, _ = multi.generate(n, normalize_weights=True, seed=11)
+    total_max = max(float(mw.max()) for mw in max_weights)
+    for w, wn in zip(weights, normed):
+        np.testing.assert_allclose(wn.cpu().numpy(), w.cpu().numpy() / total_max, rtol=1e-14)
+    # boost_to: the same fallback
+    boost = np.array([[1000.0, -2000.0, 30000.0, np.sqrt(1000.0**2 + 2000.0**2 + 30000.0**2 + D.B0_MASS**2)]])
+    flat = GenMultiDecay([(0.6, phasespace.nbody_decay(D.B0_MASS, [D.PION_MASS] * 3)),
+                          (0.4, phasespace.nbody_decay(D.B0_MASS, [D.KAON_MASS, D.PION_MASS]))])
+    w_b, mw_b, _ = flat.generate(n, normalize_weights=False, seed=2, boost_to=boost)
+    n_b, _ = flat.generate(n, normalize_weights=True, seed=2, boost_to=boost)
+    t_max = max(float(m.max()) for m in mw_b)
+    for w, wn in zip(w_b, n_b):
+        np.testing.assert_allclose(wn.cpu().numpy(), w.cpu().numpy() / t_max, rtol=1e-14)
+
+
+def test_weight_scale_is_refused_where_it_cannot_be_folded():
+    comp = phasespace.nbody_decay(D.B0_MASS, [D.PION_MASS] * 3).compile()
+    w1, _, _, _ = comp.launch(1000, seed=1)
+    w2, _, _, _ = comp.launch(1000, seed=1, weight_scale=0.25)
+    np.testing.assert_allclose(w2.cpu().numpy(), 0.25 * w1.cpu().numpy(), rtol=1e-15)
+    with pytest.raises(ValueError, match="weight_scale"):
+        comp.launch(1000, seed=1, weight_scale=0.5, normalize_weights=False)
+    with pytest.raises(ValueError, match="weight_scale"):
+        comp.launch(1000, seed=1, weight_scale=0.5, boost_to=torch.tensor([[0.0, 0.0, 100.0, 6000.0]], dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError, match="weight_scale"):
+        comp.launch(1000, seed=1, weight_scale=float("nan"))
