@@ -221,10 +221,10 @@ class CompiledDecay:
         ``weight_scale`` (normalised weights of a tree with an event-independent maximum weight only) is multiplied
         into the weights inside the kernel at no cost.
         """
-        device = _device_hint or _device()
-        n = int(n_events)
         if self.top_is_resonance and boost_to is None:
             raise ValueError("Cannot use resonance as top particle")  # ps.py:543
+        device = _device_hint or _device()
+        n = int(n_events)
         if out:
             weights, particles = out.get("weights"), out.get("particles")
             weights_max = out.get("weights_max") if not normalize_weights else None

@@ -183,3 +183,47 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
                 assert "genbod_ref" not in text and "genbod_numpy" not in text.replace("oracle/genbod_numpy.py", ""), f
+
+
+def test_compiled_tree_follows_children_added_to_a_leaf():
+    """The reference latches only decaying particles (ps.py:207-210, 318): a leaf can get children after the tree above
+    it was compiled, and the next compile() must see them (host-only: ps_tree_create needs no GPU)."""
+    kstar = GenParticle("K*0", 895.81)
+    top = GenParticle("B0", 5279.58).set_children(kstar, GenParticle("gamma", 0.0))
+    first = top.compile()
+    assert first.names == ["K*0", "gamma"] and top.compile() is first
+    other = nbody_decay(1000.0, [100.0, 100.0])  # a change elsewhere re-validates, the tree is kept
+    assert other.compile().n_particles == 2 and top.compile() is first
+    kstar.set_children(GenParticle("K+", 493.677), GenParticle("pi-", 139.57018))
+    second = top.compile()
+    assert second is not first and second.names == ["K*0", "gamma", "K+", "pi-"] and second.n_draws == 4
+
+
+def test_resonant_generating_particle_is_described_as_a_fixed_top():
+    """ps.py:534-543: with boost_to a resonance may be the particle generate() is called on; its descriptor is a fixed-mass
+    top whose mass the kernel takes from boost_to, and without boost_to the reference's ValueError stays."""
+    res = GenParticle("R", lambda min_mass, max_mass, n_events: min_mass).set_children(
+        GenParticle("a", 100.0), GenParticle("b", 200.0))
+    compiled = res.compile()
+    assert compiled.top_is_resonance and compiled.n_user == 0 and not np.isfinite(compiled.w_max)
+    with pytest.raises(ValueError, match="Cannot use resonance as top particle"):
+        compiled.launch(10, seed=1)
+    with pytest.raises(ValueError, match="Cannot use resonance as top particle"):
+        res.generate(10)
+
+
+def test_output_buffer_validation_rules():
+    from phasespace_b200.phasespace import _check_out
+
+    ok = torch.empty((3, 10, 4), dtype=torch.float64)
+    _check_out(ok, "particles", (3, 10, 4), None, pinned_host=True)
+    _check_out(torch.empty((3, 16, 4), dtype=torch.float64)[:, :10], "particles", (3, 10, 4), None, pinned_host=True, planes=True)
+    for bad, kwargs in ((torch.empty((3, 9, 4), dtype=torch.float64), {}),
+                        (torch.empty((3, 10, 4), dtype=torch.float32), {}),
+                        (torch.empty((3, 4, 10), dtype=torch.float64).permute(0, 2, 1), {"planes": True}),
+                        (torch.empty((3, 10, 8), dtype=torch.float64)[:, :, ::2], {"planes": True}),
+                        (np.empty((3, 10, 4)), {})):
+        with pytest.raises(ValueError, match="particles"):
+            _check_out(bad, "particles", (3, 10, 4), None, pinned_host=True, **kwargs)
+    with pytest.raises(ValueError, match="must be on"):
+        _check_out(ok, "particles", (3, 10, 4), torch.device("cuda", 0))
