@@ -38,7 +38,6 @@ extern "C" {
 /* generate() flags */
 #define PS_GEN_NORMALIZE 1u /* weights = w / w_max (normalize_weights=True, phasespace.py:713-717) */
 #define PS_GEN_EXACT 2u     /* reference operation order, no FMA (parity / debug variant) */
-#define PS_GEN_NO_FILTER 4u /* ps_unweight_mask: decide every candidate in fp64 (the fp32 pre-filter off; for its tests) */
 
 /* One particle of a decay tree.  The top particle has parent = -1; the children of a particle are
  * the nodes naming it as parent, in array order (GenParticle.set_children, phasespace.py:191-221). */
@@ -121,9 +120,6 @@ int ps_generate_host(const ps_tree* tree, uint64_t seed, uint64_t first_event, i
  *                      formed or stored), draws one extra uniform per event (Philox stream 1) and sets
  *                      bit (i%32) of mask[i/32] when u * w_bound < w / w_max; mask holds (n_events+31)/32
  *                      words and every one of them is written (bits past n_events are 0).
- *                      Flat decays of fixed masses are decided by an fp32 evaluation of the weight with a rigorous
- *                      per-event error bound wherever that is conclusive (all but ~1e-4 of the candidates) and in
- *                      fp64 otherwise: the mask is bit-identical to the all-fp64 one (PS_GEN_NO_FILTER).
  *                      overflow (device uint64, caller-zeroed, may be NULL) is incremented once per candidate
  *                      with w / w_max > w_bound: those are accepted with probability 1 instead of > 1, so a
  *                      non-zero count means w_bound was too small and the accepted sample is biased.

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PS_B200_LIB") or os.path.join(_HERE, "libphasespace_b200.so")
 
 PS_MASS_FIXED, PS_MASS_GAUSS, PS_MASS_BW, PS_MASS_RELBW, PS_MASS_USER = range(5)
-PS_GEN_NORMALIZE, PS_GEN_EXACT, PS_GEN_NO_FILTER = 1, 2, 4
+PS_GEN_NORMALIZE, PS_GEN_EXACT = 1, 2
 PS_E_INVALID, PS_E_CUDA, PS_E_COMPILE, PS_E_FORBIDDEN = -1, -2, -3, -4
 TILE = 256  # events per tile of the unweighting mask kernel
 ABI_VERSION = 3  # PS_ABI_VERSION of include/phasespace_b200.h this binding was written against

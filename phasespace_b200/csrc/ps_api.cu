@@ -367,27 +367,6 @@ extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tre
         t->base.wmax_const = t->w_max;
         t->base.inv_wmax_const = 1.0 / t->w_max;
     }
-    // constants of the fp32 pre-filter of the mask pass (PsParams::mk_*): flat decay of fixed masses
-    {
-        const std::vector<int>& ch = t->children[t->top];
-        bool flat = !t->has_grandchildren && !t->resonant_leaf && ch.size() >= 3;
-        for (int c : ch) flat = flat && nodes[c].kind == PS_MASS_FIXED;
-        const double M = nodes[t->top].mass;
-        double msum = 0.0;
-        for (int c : ch) msum += nodes[c].mass;
-        if (flat && std::isfinite(t->w_max) && t->w_max > 0.0 && M > 0.0 && M - msum > 0.0) {
-            double run = 0.0;
-            for (size_t j = 0; j < ch.size(); ++j) {
-                run += nodes[ch[j]].mass;
-                t->base.mk_two_c[j] = (float)(2.0 * nodes[ch[j]].mass / M);
-                t->base.mk_S[j] = (float)(run / M);
-            }
-            t->base.mk_avail = (float)((M - msum) / M);
-            const double norm = std::pow(M, (double)ch.size() - 1.0) / t->w_max;
-            t->base.mk_norm = (float)norm;
-            t->base.mk_valid = (std::isfinite(norm) && norm < 1e30 && norm > 1e-30) ? 1 : 0;
-        }
-    }
     *out = t;
     return 0;
 }
@@ -1046,7 +1025,6 @@ extern "C" int ps_unweight_mask(const ps_tree* tree, uint64_t seed, uint64_t fir
     if (rc) return rc;
     if (n_events == 0) return 0;
     const void* fn = nullptr;
-    if (flags & PS_GEN_NO_FILTER) p.mk_valid = 0;
     rc = get_kernel(tree, PS_VARIANT_MASK, 0, 0, (flags & PS_GEN_EXACT) ? 1 : 0, &fn);
     if (rc) return rc;
     int sms = 0;

@@ -73,7 +73,6 @@ struct Pt {
     static constexpr bool resonant_leaf_below =
         (false || ... || ((Ch::nch == 0 && Ch::kind != PS_KIND_FIXED) || Ch::resonant_leaf_below));
     static constexpr bool has_grandchildren = (false || ... || (Ch::nch > 0));
-    static constexpr bool all_children_fixed = (true && ... && (Ch::kind == PS_KIND_FIXED));
     // every decay in the tree is a two-body decay (few instructions per byte written: memory-bound, see genbod_body)
     static constexpr bool two_body_only = (sizeof...(Ch) == 0 || sizeof...(Ch) == 2) && (true && ... && Ch::two_body_only);
     template <int J>
@@ -1176,118 +1175,6 @@ __global__ void __launch_bounds__(PS_BLOCK, PS_MIN_BLOCKS) genbod_kernel(const _
 // overflow (optional): number of candidates whose normalised weight exceeds w_bound -- such an event is accepted with
 // probability 1 instead of w / w_bound > 1, i.e. the bound was too small and the sample is biased by exactly those
 // events.  One compare and one ballot per event; the atomic only fires for warps that saw one.
-// ------------------------------------------------------------------ fp32 pre-filter of the mask pass
-// Nine tenths of the candidates of a many-body decay are rejected, and whether u w_bound < w / w_max holds is almost never
-// a close call: an fp32 evaluation of the weight with a rigorous error bound decides all but ~1e-4 of the candidates, at
-// one issue slot per instruction instead of 2.18 for fp64.  Flat decays of fixed masses at rest only (PsParams::mk_*).
-//   * the sorted uniforms r_j are taken as the top 23 bits of the 51-bit draws (truncation: monotone, so the order is the
-//     fp64 one; |error| < 2^-23 each);
-//   * the cancelling factor of the two-body momentum is formed where it does not cancel: a - b - c = (r_{j+1} - r_j) avail
-//     exactly, so x_j = d (d + 2c)(d + 2b)(d + 2b + 2c) with d = (r_{j+1} - r_j) avail is a product of sums of positive
-//     terms.  Its relative error is <= 8.3 rho_j + 1e-6 with rho_j = 2^-23 / (r_{j+1} - r_j): the only large term is the
-//     truncation of the spacing itself;
-//   * relative error of the normalised weight: delta <= sum_j (4.2 + 2) rho_j + 3e-6  (square roots halve, the
-//     denominators 2 a_j add 2 rho_j each, ~40 roundings of 2^-24, the approximate reciprocal square root 2^-22).  The
-//     code uses delta = 1.5e-6 sum_j 1/(r_{j+1} - r_j) + 3e-5, twice that, and gives up (fp64) when delta > 1/4;
-//   * the acceptance draw u is known to within [u32, u32 + 2^-23): accept if even the largest possible u w_bound lies
-//     below the smallest possible weight, reject if the smallest lies above the largest, else decide in fp64.
-// The result is bit-identical to the all-fp64 mask (tests/test_unweight_gpu.py compares the two on 1.3e8 candidates).
-__device__ __forceinline__ void cmp_exchange(float& a, float& b) {
-    const float lo = fminf(a, b), hi = fmaxf(a, b);
-    a = lo, b = hi;
-}
-template <int K>
-__device__ __forceinline__ void sort_network_f32(float (&r)[K]) {
-#define PS_CE(i, j) cmp_exchange(r[i], r[j])
-    if constexpr (K == 1) {
-    } else if constexpr (K == 2) {
-        PS_CE(0, 1);
-    } else if constexpr (K == 3) {
-        PS_CE(0, 2); PS_CE(0, 1); PS_CE(1, 2);
-    } else if constexpr (K == 4) {
-        PS_CE(0, 2); PS_CE(1, 3); PS_CE(0, 1); PS_CE(2, 3); PS_CE(1, 2);
-    } else if constexpr (K == 5) {
-        PS_CE(0, 3); PS_CE(1, 4); PS_CE(0, 2); PS_CE(1, 3); PS_CE(0, 1); PS_CE(2, 4); PS_CE(1, 2); PS_CE(3, 4); PS_CE(2, 3);
-    } else if constexpr (K == 6) {
-        PS_CE(0, 5); PS_CE(1, 3); PS_CE(2, 4); PS_CE(1, 2); PS_CE(3, 4); PS_CE(0, 3); PS_CE(2, 5); PS_CE(0, 1); PS_CE(2, 3);
-        PS_CE(4, 5); PS_CE(1, 2); PS_CE(3, 4);
-    } else if constexpr (K == 7) {
-        PS_CE(0, 6); PS_CE(2, 3); PS_CE(4, 5); PS_CE(0, 2); PS_CE(1, 4); PS_CE(3, 6); PS_CE(0, 1); PS_CE(2, 5); PS_CE(3, 4);
-        PS_CE(1, 2); PS_CE(4, 6); PS_CE(2, 3); PS_CE(4, 5); PS_CE(1, 2); PS_CE(3, 4); PS_CE(5, 6);
-    } else if constexpr (K == 8) {
-        PS_CE(0, 2); PS_CE(1, 3); PS_CE(4, 6); PS_CE(5, 7); PS_CE(0, 4); PS_CE(1, 5); PS_CE(2, 6); PS_CE(3, 7); PS_CE(0, 1);
-        PS_CE(2, 3); PS_CE(4, 5); PS_CE(6, 7); PS_CE(2, 4); PS_CE(3, 5); PS_CE(1, 4); PS_CE(3, 6); PS_CE(1, 2); PS_CE(3, 4);
-        PS_CE(5, 6);
-    } else {
-#pragma unroll
-        for (int i = 1; i < K; ++i) {
-#pragma unroll
-            for (int j = i; j > 0; --j) PS_CE(j - 1, j);
-        }
-    }
-#undef PS_CE
-}
-
-// the top 23 bits of a draw's 51-bit field as a float in [0, 1): d = 1 + u/2 holds the field in its low 51 mantissa bits
-__device__ __forceinline__ float draw_top23(double d) {
-    const unsigned int hi = (unsigned int)__double2hiint(d), lo = (unsigned int)__double2loint(d);
-    const unsigned int bits = __funnelshift_l(lo, hi, 4);  // (hi << 4) | (lo >> 28)
-    return __uint_as_float((bits & 0x007FFFFFu) | 0x3F800000u) - 1.0f;
-}
-
-template <int BASE, class C, int... I>
-__device__ __forceinline__ void fetch_draws_top23(C& c, float* s, Seq<I...>) {
-    ((s[I] = draw_top23(c.template mantissa<BASE + I>())), ...);
-}
-
-// Returns 1: surely accepted, 0: surely rejected, -1: not conclusive (decide in fp64).  u32: top 23 bits of the acceptance draw.
-template <class Tree, class C>
-__device__ __forceinline__ int mask_filter_f32(C& c, const PsParams& prm, float w_bound, float u32) {
-    constexpr int N = Tree::nch;
-    float r[N];
-    r[0] = 0.0f;
-    r[N - 1] = 1.0f;
-    {
-        float s[N - 2];
-        fetch_draws_top23<Tree::ucol>(c, s, MakeSeq<N - 2>{});
-        sort_network_f32<N - 2>(s);
-#pragma unroll
-        for (int j = 0; j < N - 2; ++j) r[j + 1] = s[j];
-    }
-    const float avail = prm.mk_avail;
-    float px = 1.0f, pe = 1.0f, sum_inv = 0.0f;
-#pragma unroll
-    for (int j = 0; j < N - 1; ++j) {
-        const float dr = r[j + 1] - r[j];  // exact: both are multiples of 2^-23 below 1 (or 0, or 1)
-        float inv_dr;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_dr) : "f"(dr));
-        sum_inv += inv_dr;  // +inf for a zero spacing: not conclusive
-        const float d = dr * avail;
-        const float two_c = prm.mk_two_c[j + 1];
-        const float b = j == 0 ? prm.mk_S[0] : fmaf(r[j], avail, prm.mk_S[j]);
-        const float f2 = d + two_c, f3 = fmaf(2.0f, b, d);
-        const float f4 = f3 + two_c;
-        const float x = (d * f2) * (f3 * f4);
-        px = j == 0 ? x : px * x;
-        const float two_a = f4 + d;
-        pe = j == 0 ? two_a : pe * two_a;
-    }
-    float rs, rpe;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(px));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rpe) : "f"(pe));
-    const float w = prm.mk_norm * (px * rs) * rpe;  // normalised weight w / w_max
-    const float delta = fmaf(1.5e-6f, sum_inv, 3e-5f);
-    const float lo = w * (1.0f - delta), hi = w * (1.0f + delta);
-    const float t_lo = u32 * w_bound * (1.0f - 4e-7f), t_hi = (u32 + 1.1920929e-7f) * w_bound * (1.0f + 4e-7f);
-    // not conclusive: a tiny spacing (delta > 1/4, or inf / NaN), an underflowed product, or a weight that could exceed
-    // the bound itself (the overflow counter is kept in fp64)
-    const bool usable = delta < 0.25f && px > 1e-30f && hi * (1.0f + 1e-6f) < w_bound;
-    if (!usable) return -1;
-    if (t_hi < lo) return 1;
-    if (t_lo > hi) return 0;
-    return -1;
-}
-
 template <class Tree, bool BOOST>
 __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_bound, unsigned int* mask,
                                                  unsigned long long* overflow) {
@@ -1306,40 +1193,24 @@ __device__ __forceinline__ void genbod_mask_body(const PsParams& prm, double w_b
             c.event = prm.first_event + (unsigned long long)i;
             c.dbg_row = nullptr;
             c.bad = false;
-            const Philox4 acc = use_keyed_philox<Tree>() ? philox4x32_10_keyed(prm.philox_keys, c.event, 0u, 1u)
-                                                          : philox4x32_10(prm.seed, c.event, 0u, 1u);
-            int verdict = -1;
-            // fp32 pre-filter (flat decays of fixed masses at rest): see mask_filter_f32
-            constexpr bool F32 = !PS_EXACT && !BOOST && Tree::nch >= 3 && !Tree::has_grandchildren && Tree::all_children_fixed;
-            if constexpr (F32) {
-                if (prm.mk_valid) {
-                    // top 23 bits of the 51-bit acceptance field (uniform_from_bits: lo word + low 19 bits of the next)
-                    const unsigned int top = ((acc.w[1] & 0x7FFFFu) << 4) | (acc.w[0] >> 28);
-                    const float u32 = __uint_as_float(top | 0x3F800000u) - 1.0f;
-                    verdict = mask_filter_f32<Tree>(c, prm, (float)w_bound, u32);
-                }
-            }
-            if (verdict >= 0) {
-                accept = verdict != 0;
-            } else {
-                double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
-                if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
-                const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
-                double w_max, inv_w_max;
-                event_w_max<Tree, BOOST>(c, prm, bx, by, bz, be, false, w_max, inv_w_max);
-                const double u = uniform_from_bits(acc.w[0], acc.w[1]);
+            double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
+            if constexpr (BOOST) load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
+            const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
+            double w_max, inv_w_max;
+            event_w_max<Tree, BOOST>(c, prm, bx, by, bz, be, false, w_max, inv_w_max);
+            const double u = use_keyed_philox<Tree>() ? philox_uniform0_keyed(prm.philox_keys, c.event, 1u)
+                                                      : philox_uniform0(prm.seed, c.event, 1u);
 #if PS_EXACT
-                accept = u * w_bound * w_max < w;
-                over = w_bound * w_max < w;
+            accept = u * w_bound * w_max < w;
+            over = w_bound * w_max < w;
 #else
-                // w = 1 / c.wacc.inverse(): u w_bound < w / w_max  <=>  u w_bound / w < 1 / w_max  (w = 0: inf, rejected)
-                const double bound_over_w = w_bound * c.wacc.inverse();
-                accept = u * bound_over_w < inv_w_max;
-                over = bound_over_w < inv_w_max;
-                (void)w;
+            // w = 1 / c.wacc.inverse(): u w_bound < w / w_max  <=>  u w_bound / w < 1 / w_max  (w = 0: inf, rejected)
+            const double bound_over_w = w_bound * c.wacc.inverse();
+            accept = u * bound_over_w < inv_w_max;
+            over = bound_over_w < inv_w_max;
+            (void)w;
 #endif
-                bad_any |= c.bad;
-            }
+            bad_any |= c.bad;
         }
         const unsigned int word = __ballot_sync(0xffffffffu, accept);
         const unsigned int over_word = __ballot_sync(0xffffffffu, over);

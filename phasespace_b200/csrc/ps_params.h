@@ -71,15 +71,6 @@ typedef struct PsParams {
     int* err_flag;
     int normalize; /* 1: weights = w / w_max ; 0: weights = w and weights_max = w_max */
     int tiles_per_cta; /* chunked grid only: CTA b takes tiles [b*K, (b+1)*K) */
-
-    /* fp32 pre-filter of the unweighting mask pass (ps_kernel.cuh: mask_filter_f32), flat decays of fixed masses at rest
-     * only: child masses in units of the top mass M.  mk_two_c[j] = 2 m_j / M, mk_S[j] = (m_0 + ... + m_j) / M,
-     * mk_avail = (M - sum m) / M, mk_norm = M^(n-1) / w_max.  mk_valid = 0 switches the filter off. */
-    float mk_two_c[PS_MAX_SLOTS];
-    float mk_S[PS_MAX_SLOTS];
-    float mk_avail, mk_norm;
-    int mk_valid;
-    int mk_pad_;
 } PsParams;
 
 #endif

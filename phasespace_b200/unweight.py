@@ -29,8 +29,7 @@ class UnweightingOverflowError(RuntimeError):
 
 
 def generate_unweighted(decay, n_events: int, seed: int, *, w_bound: float = 1.0, first_event: int = 0,
-                        exact: bool = False, return_overflow: bool = False, on_overflow: str = "raise",
-                        _no_filter: bool = False):
+                        exact: bool = False, return_overflow: bool = False, on_overflow: str = "raise"):
     """Unweighted events among the candidates ``[first_event, first_event + n_events)`` of stream ``seed``.
 
     ``w_bound`` is the acceptance bound on the *normalised* weight ``w / w_max`` (1.0 is always safe; a
@@ -59,7 +58,7 @@ def generate_unweighted(decay, n_events: int, seed: int, *, w_bound: float = 1.0
     # [accepted count (int64) | error flag (int32, low half of the word) | overflow count]: one read-back for all
     state = torch.zeros((3,), dtype=torch.int64, device=device)
     total, err, over = state[:1], state[1:2].view(torch.int32)[:1], state[2:]
-    flags = (_lib.PS_GEN_EXACT if exact else 0) | (_lib.PS_GEN_NO_FILTER if _no_filter else 0)
+    flags = _lib.PS_GEN_EXACT if exact else 0
     seed = int(seed) & (2**64 - 1)
     if n > 0:
         _lib.check(lib.ps_unweight_mask(compiled.handle, seed, int(first_event), n, float(w_bound), _ptr(mask),
@@ -87,7 +86,7 @@ def generate_unweighted(decay, n_events: int, seed: int, *, w_bound: float = 1.0
         _lib.check(lib.ps_unweight_index(_ptr(mask), _ptr(offsets), int(first_event), n, _ptr(index), stream))
         _lib.check(lib.ps_generate_indexed(
             compiled.handle, seed, _ptr(index), n_acc, None, 0, None, _ptr(weights), None, _ptr(slab),
-            int(4 * max(cap, 1)), None, _ptr(err), (flags & _lib.PS_GEN_EXACT) | _lib.PS_GEN_NORMALIZE, stream))
+            int(4 * max(cap, 1)), None, _ptr(err), flags | _lib.PS_GEN_NORMALIZE, stream))
     slab = slab[:, :n_acc]
     parts = {name: slab[compiled.slots[name]] for name in compiled.names}
     if return_overflow:

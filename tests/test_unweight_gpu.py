@@ -156,28 +156,3 @@ def test_unweighting_parity_at_1e8_candidates():
     total = sum(parts.values())
     assert float(total[:, :3].abs().max()) / D.B0_MASS < 1e-12
     assert float((total[:, 3] - D.B0_MASS).abs().max()) / D.B0_MASS < 1e-12
-
-
-@pytest.mark.parametrize("n_body,masses,w_bound_factor,n", [
-    (10, None, 1.5, 1 << 27),           # BASELINE config 5's chunk
-    (10, None, 0.7, 20_000_003),        # a bound below the maximum: the overflow counter must agree too
-    (3, None, 1.0, 30_000_000),
-    (4, [D.KAON_MASS, D.PION_MASS, 0.0, 105.6583755], 1.2, 30_000_000),   # a massless product
-    (6, [0.0] * 6, 1.5, 20_000_000),    # all massless: the sums of positive terms degenerate to the spacings alone
-    (12, None, 1.5, 10_000_000),        # a tree compiled by NVRTC
-])
-def test_fp32_prefilter_gives_the_fp64_mask(n_body, masses, w_bound_factor, n):
-    """The mask pass decides most candidates of a flat decay from an fp32 evaluation of the weight with a per-event error
-    bound and falls back to fp64 where that is not conclusive: the accepted list and the overflow count must be
-    IDENTICAL to those of the all-fp64 pass (PS_GEN_NO_FILTER), for every tree, bound and size."""
-    seed, first = 31, 123_456_789_012
-    decay = phasespace.nbody_decay(D.B0_MASS, masses or [D.PION_MASS] * n_body)
-    stats = torch.zeros(4, dtype=torch.float64, device="cuda")
-    decay.compile().launch(2_000_000, seed + 1, stats=stats)
-    w_bound = min(1.0, w_bound_factor * float(stats[0]))
-    a_parts, a_idx, a_w, a_over = generate_unweighted(decay, n, seed, w_bound=w_bound, first_event=first, return_overflow=True)
-    del a_parts
-    b_parts, b_idx, b_w, b_over = generate_unweighted(decay, n, seed, w_bound=w_bound, first_event=first, return_overflow=True,
-                                                      _no_filter=True)
-    assert a_idx.numel() > 0 and torch.equal(a_idx, b_idx) and torch.equal(a_w, b_w) and a_over == b_over
-    assert (a_over > 0) == (w_bound_factor < 1.0)
