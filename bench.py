@@ -285,7 +285,10 @@ def run_b200(args, rank, local_rank, world):
     sampler.start()
 
     def timed_launches(step, reps, warmup=2):
-        """CUDA-event time per launch of `step` (ms, max over ranks) over `reps` back-to-back launches + clocks."""
+        """CUDA-event time per launch of `step` (ms, max over ranks) over `reps` back-to-back launches + clocks.
+        Every config starts from an idle, cooled board (1 s), like the headline: a burst figure at full clock."""
+        barrier()
+        time.sleep(1.0)
         for _ in range(warmup):
             step(0)
         barrier()
@@ -372,45 +375,6 @@ def run_b200(args, rank, local_rank, world):
     n_acc = float(world) * n
     global_stats = {"max_w": float(gstats[0]), "mean_w": float(gstats[1]) / n_acc,
                     "how": "kernel epilogue (warp shuffle -> shared -> one atomic per CTA) + two 16-byte all-reduces"}
-
-    # ================================================================== sustained: the same launches for >= 2 s
-    sustained = None
-    if not args.no_sustained:
-        barrier()
-        time.sleep(0.2)
-        batch = max(10, int(0.05 / max(kernel_ms * 1e-3, 1e-6)))  # ~50 ms of launches between two host checks
-        marks = [torch.cuda.Event(enable_timing=True)]
-        w0 = time.perf_counter()
-        marks[0].record(stream)
-        done = 0
-        while time.perf_counter() - w0 < args.sustained_seconds:
-            for _ in range(batch):
-                step()
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record(stream)
-            marks.append(ev)
-            done += batch
-            ev.synchronize()
-        w1 = time.perf_counter()
-        total = marks[0].elapsed_time(marks[-1])
-        q = max(1, (len(marks) - 1) // 4)
-        last_q = marks[-1 - q].elapsed_time(marks[-1]) / (q * batch)
-        sus_ms = max_over_ranks(total / done)
-        sus_last = max_over_ranks(last_q)
-        sus_clocks = sampler.summary(w0 + 0.5 * (w1 - w0), w1)  # second half: the power cap has settled by then
-        sustained = {
-            "what": "the headline launches issued back to back (host check every ~50 ms) until the wall clock passes "
-                    "sustained_seconds; the board reaches its power cap after ~0.3 s, so this is what a long job sees",
-            "seconds": total * 1e-3, "steps": done, "ms_per_step": sus_ms, "events_per_s": world * n / (sus_ms * 1e-3),
-            "achieved_gbs": BYTES_PER_EVENT * n / (sus_ms * 1e-3) / 1e9, "frac": BYTES_PER_EVENT * n / (sus_ms * 1e-3) / 1e9 / peak,
-            "ms_per_step_last_quarter": sus_last, "frac_last_quarter": BYTES_PER_EVENT * n / (sus_last * 1e-3) / 1e9 / peak,
-            "clocks_second_half": sus_clocks,
-        }
-        if peaks and "bf16_tflops_sustained" in peaks:
-            sustained["note"] = ("peak is the driver's burst copy figure; the driver's own sustained/burst ratio for bf16 "
-                                 f"matmul on this pool is {peaks['bf16_tflops_sustained'] / peaks['bf16_tflops']:.2f}")
-    del out
-    torch.cuda.empty_cache()
 
     # ================================================================== all five BASELINE.json configs
     configs = {}
@@ -585,6 +549,7 @@ def run_b200(args, rank, local_rank, world):
 
         generate_unweighted(d5, min(chunk, per_gpu), args.seed, w_bound=w_bound, first_event=first5, return_overflow=True)
         barrier()
+        time.sleep(1.0)
         a5, b5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         l0 = _lib.lib.ps_launch_count()
@@ -611,6 +576,45 @@ def run_b200(args, rank, local_rank, world):
                       "max over ranks", "clocks": sampler.summary(w0, w1), "all_events_stored": stored}
         assert over_all == 0, f"{over_all} candidates exceeded the acceptance bound"
         torch.cuda.empty_cache()
+
+    # ================================================================== sustained: the same launches for >= 2 s
+    sustained = None
+    if not args.no_sustained:
+        barrier()
+        time.sleep(0.2)
+        batch = max(10, int(0.05 / max(kernel_ms * 1e-3, 1e-6)))  # ~50 ms of launches between two host checks
+        marks = [torch.cuda.Event(enable_timing=True)]
+        w0 = time.perf_counter()
+        marks[0].record(stream)
+        done = 0
+        while time.perf_counter() - w0 < args.sustained_seconds:
+            for _ in range(batch):
+                step()
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            marks.append(ev)
+            done += batch
+            ev.synchronize()
+        w1 = time.perf_counter()
+        total = marks[0].elapsed_time(marks[-1])
+        q = max(1, (len(marks) - 1) // 4)
+        last_q = marks[-1 - q].elapsed_time(marks[-1]) / (q * batch)
+        sus_ms = max_over_ranks(total / done)
+        sus_last = max_over_ranks(last_q)
+        sus_clocks = sampler.summary(w0 + 0.5 * (w1 - w0), w1)  # second half: the power cap has settled by then
+        sustained = {
+            "what": "the headline launches issued back to back (host check every ~50 ms) until the wall clock passes "
+                    "sustained_seconds; the board reaches its power cap after ~0.3 s, so this is what a long job sees",
+            "seconds": total * 1e-3, "steps": done, "ms_per_step": sus_ms, "events_per_s": world * n / (sus_ms * 1e-3),
+            "achieved_gbs": BYTES_PER_EVENT * n / (sus_ms * 1e-3) / 1e9, "frac": BYTES_PER_EVENT * n / (sus_ms * 1e-3) / 1e9 / peak,
+            "ms_per_step_last_quarter": sus_last, "frac_last_quarter": BYTES_PER_EVENT * n / (sus_last * 1e-3) / 1e9 / peak,
+            "clocks_second_half": sus_clocks,
+        }
+        if peaks and "bf16_tflops_sustained" in peaks:
+            sustained["note"] = ("peak is the driver's burst copy figure; the driver's own sustained/burst ratio for bf16 "
+                                 f"matmul on this pool is {peaks['bf16_tflops_sustained'] / peaks['bf16_tflops']:.2f}")
+    del out
+    torch.cuda.empty_cache()
 
     # ================================================================== e2e: public host-delivery call
     e2e = None
