@@ -286,7 +286,8 @@ def run_b200(args, rank, local_rank, world):
 
     def timed_launches(step, reps, warmup=2):
         """CUDA-event time per launch of `step` (ms, max over ranks) over `reps` back-to-back launches + clocks.
-        Every config starts from an idle, cooled board (1 s), like the headline: a burst figure at full clock."""
+        Every config starts from an idle, cooled board (1 s) and its timed region lasts 30-50 ms, like the headline's:
+        a burst figure at full clock (the board's power limit starts to bite after ~50-100 ms of load)."""
         barrier()
         time.sleep(1.0)
         for _ in range(warmup):
@@ -442,7 +443,7 @@ def run_b200(args, rank, local_rank, world):
               "particles": torch.empty((4, n3, 4), dtype=torch.float64, device=device)}
         err.zero_()
         ms, clk = timed_launches(lambda k: c3.launch(n3, seed=args.seed, first_event=rank * n3, boost_to=boost, out=o3, err=err),
-                                 reps=30)
+                                 reps=10)
         assert int(err.item()) == 0
         ev_s = world * n3 / (ms * 1e-3)
         configs["3_four_body_boost_1e8"] = {
@@ -489,7 +490,7 @@ def run_b200(args, rank, local_rank, world):
         o4 = {"weights": torch.empty((n4,), dtype=torch.float64, device=device),
               "particles": torch.empty((4, n4, 4), dtype=torch.float64, device=device)}
         err.zero_()
-        ms, clk = timed_launches(lambda k: c4.launch(n4, seed=args.seed, first_event=rank * n4, out=o4, err=err), reps=30)
+        ms, clk = timed_launches(lambda k: c4.launch(n4, seed=args.seed, first_event=rank * n4, out=o4, err=err), reps=10)
         assert int(err.item()) == 0
         ev_s = world * n4 / (ms * 1e-3)
         entry = {"workload": "B0->K*0(->K+ pi-) gamma, K*0 ~ relativistic Breit-Wigner(895.81, 47.4) sampled in the "
