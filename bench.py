@@ -575,7 +575,8 @@ def run_b200(args, rank, local_rank, world):
             "bytes_stored_per_accepted_event": 8 + 8 + 320, "gpu_launches": int(l5),
             "timing": "CUDA events around the whole chunk loop (host read-back of the accepted count per chunk included), "
                       "max over ranks", "clocks": sampler.summary(w0, w1), "all_events_stored": stored}
-        assert over_all == 0, f"{over_all} candidates exceeded the acceptance bound"
+        # (reported, not asserted: a bench line with a non-zero count says the bound must be raised, it must not get lost)
+        configs["5_ten_body_unweighting"]["unbiased"] = bool(over_all == 0)
         torch.cuda.empty_cache()
 
     # ================================================================== sustained: the same launches for >= 2 s
