@@ -30,19 +30,24 @@ _DEVICES: dict = {}
 
 
 def _device() -> torch.device:
-    """The current CUDA device.  (torch.cuda.is_available() costs microseconds per call: asked once per process.)"""
+    """The current CUDA device.  (torch.cuda.is_available() costs microseconds per call: asked once per process; after
+    that the device index comes from the binding underneath torch.cuda.current_device(), without its lazy-init check.)"""
     global _CUDA_CHECKED
     if not _CUDA_CHECKED:
         if not torch.cuda.is_available():
             raise RuntimeError(
                 "phasespace_b200 needs a CUDA device (B200, sm_100a): there is no CPU implementation of the generator."
             )
+        torch.cuda.current_device()  # initialises torch's CUDA state
         _CUDA_CHECKED = True
-    index = torch.cuda.current_device()
+    index = _current_device_index()
     dev = _DEVICES.get(index)
     if dev is None:
         dev = _DEVICES[index] = torch.device("cuda", index)
     return dev
+
+
+_current_device_index = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
 
 
 try:  # the raw cudaStream_t of torch's current stream without building a Stream object (what Triton's launcher uses)
@@ -152,6 +157,11 @@ class CompiledDecay:
         self.epoch = _TREE_EPOCH
         self._err_flags = {}
         self._static_forbidden = self._check_static()
+        # the plain call of generate(): no per-event failure mode, no Python mass functions, nothing forbidden
+        self.plain_ok = (not self.has_resonances and not self.top_is_resonance and self.n_user == 0
+                         and self._static_forbidden is None)
+        self._slot_items = tuple((name, self.slots[name]) for name in self.names)
+        self._generate_c = _lib.lib.ps_generate
 
     def __del__(self):
         try:
@@ -209,6 +219,24 @@ class CompiledDecay:
 
         node(self.top, top_mass)
         return out
+
+    def generate_plain(self, n: int, seed: int, first_event: int, device):
+        """``generate(n)`` of a tree at rest with fixed masses, normalised weights: one allocation
+        ``[particles (P, n, 4) | weights (n)]``, one C-ABI call, the views.  (The general path is :meth:`launch`.)"""
+        n_part = self.n_particles
+        buf = torch.empty(((4 * n_part + 1) * n,), dtype=torch.float64, device=device)
+        base = buf.data_ptr()
+        err = self._err_flags.get(device)
+        if err is None:
+            err = self._err_flags[device] = torch.zeros((1,), dtype=torch.int32, device=device)
+        rc = self._generate_c(self.handle, seed, first_event, n, None, 0, None, None, base + 32 * n_part * n, None, base,
+                              4 * n, None, err.data_ptr(), _lib.PS_GEN_NORMALIZE, _raw_current_stream(device.index), 1.0)
+        if rc:
+            _lib.check(rc)
+        # one view per output straight off the buffer (as_strided: half the cost of slicing, reshaping and indexing)
+        plane = 4 * n
+        return (torch.as_strided(buf, (n,), (1,), n_part * plane),
+                {name: torch.as_strided(buf, (n, 4), (4, 1), slot * plane) for name, slot in self._slot_items})
 
     # ------------------------------------------------------------------ the one C-ABI call
     def launch(self, n_events: int, seed: int, first_event: int = 0, boost_to=None, normalize_weights=True,
@@ -449,6 +477,13 @@ class GenParticle:
         if isinstance(n_events, torch.Tensor):
             n_events = int(n_events.item())
         n_events = int(n_events)
+        # The plain call -- events at rest, normalised weights, tensors out, a tree that cannot fail per event -- goes
+        # straight to the C ABI: a 1e6-event launch lasts ~13 us on a B200, so every microsecond of host work shows.
+        if (boost_to is None and normalize_weights and debug_uniforms is None and not as_vectors and not exact
+                and _weight_scale == 1.0 and n_events > 0):
+            compiled = self._compiled
+            if compiled is not None and compiled.epoch == _TREE_EPOCH and compiled.plain_ok:
+                return compiled.generate_plain(n_events, rng.seed, rng.reserve(n_events), device)
         if boost_to is not None:
             boost_to = _convert_boost(boost_to, device)
             if boost_to.ndim == 1:

@@ -26,10 +26,12 @@ _MASK64 = (1 << 64) - 1
 class Generator:
     """Counter-based generator state: ``seed`` and the index of the next unused event."""
 
+    __slots__ = ("seed", "offset")
+    _lock = threading.Lock()  # one lock for all generators: reserve() holds it for two additions
+
     def __init__(self, seed: int, offset: int = 0):
         self.seed = int(seed) & _MASK64
         self.offset = int(offset)
-        self._lock = threading.Lock()
 
     @classmethod
     def from_seed(cls, seed: int) -> "Generator":
@@ -125,6 +127,8 @@ def get_rng(seed: SeedLike = None) -> Generator:
     """Get or create a generator (reference: random.py:14-40)."""
     if seed is None:
         return _GLOBAL
+    if type(seed) is int:  # the common case of a seeded call, first: a small call's host time shows (bench config 1)
+        return Generator(seed)
     if isinstance(seed, Generator):
         return seed
     if isinstance(seed, torch.Tensor):
