@@ -75,6 +75,10 @@ double ps_tree_w_max(const ps_tree* tree);
 /* Canonical C++ type of the tree (the kernel template argument) and whether a kernel for it was
  * compiled ahead of time (otherwise the first ps_generate JIT-compiles it with NVRTC). */
 const char* ps_tree_signature(const ps_tree* tree);
+/* Nodes of the inverse-CDF table built for a relativistic Breit-Wigner resonance whose mass limits are the same for every
+ * event (the first resonance below a top particle at rest), 0 if the tree has none: with a table that resonance is sampled
+ * without transcendental functions (ps_samplers.cuh sample_relbw_table; mass_functions.py:70-102). */
+int32_t ps_tree_relbw_nodes(const ps_tree* tree);
 int32_t ps_tree_is_aot(const ps_tree* tree, int32_t with_boost, int32_t with_debug_uniforms, uint32_t flags);
 
 /* Replaces GenParticle.generate / _recursive_generate / _generate / _generate_part2

@@ -104,6 +104,12 @@ struct ps_tree {
     // not pay for a mutex and a map lookup keyed on a hundred-character string every time
     mutable std::atomic<const void*> kernel_cache[3][2][2][2] = {};
     mutable std::atomic<int> blocks_per_sm_cache[3][2][2][2] = {};
+    // nodes of the inverse CDF of a relativistic Breit-Wigner with event-independent limits (PsParams::relbw_tab): built
+    // once on the host, copied to each device at the first launch there
+    std::vector<double> relbw_nodes;
+    int relbw_mlog = 0, relbw_J_lo = 0, relbw_J_hi = 0;
+    mutable std::mutex relbw_mu;
+    mutable std::map<int, double*> relbw_dev;
     mutable std::atomic<unsigned long long> one_cta_ready[2][2] = {};  // [dbg][exact]: devices (bit mask) on which the shared-memory attribute is set (pick_grid)
 };
 
@@ -239,6 +245,87 @@ void host_sampler_limits(int kind, double mass, double width, const double sc[5]
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------- relBW node table
+// ps_samplers.cuh sample_relbw_table: for a relativistic Breit-Wigner whose limits are the same for every event, solve
+// G(z) = G_lo + u dG at the nodes u_k once (long double Newton from the neighbouring node, bisection as a safeguard).
+namespace {
+
+long double relbw_G(long double z, long double kappa) {
+    const long double y = z + kappa;
+    return atanl(z) + atanl(y) + logl((y * y + 1.0L) / (z * z + 1.0L)) / kappa;
+}
+
+long double relbw_root(long double target, long double kappa, long double z_lo, long double z_hi, long double z) {
+    const long double k2 = kappa * kappa + 4.0L;
+    z = z < z_lo ? z_lo : (z > z_hi ? z_hi : z);
+    for (int it = 0; it < 40; ++it) {
+        const long double y = z + kappa;
+        const long double step = (relbw_G(z, kappa) - target) * (z * z + 1.0L) * (y * y + 1.0L) / k2;
+        long double zn = z - step;
+        zn = zn < z_lo ? z_lo : (zn > z_hi ? z_hi : zn);
+        // quadratic convergence: a step below 1e-10 leaves an error below 1e-19, the noise floor of the 64-bit mantissa
+        if (fabsl(zn - z) <= 1e-10L * (1.0L + fabsl(zn))) return zn;
+        z = zn;
+    }
+    long double a = z_lo, b = z_hi;  // Newton did not settle (never seen): bisection
+    for (int it = 0; it < 200; ++it) {
+        const long double mid = 0.5L * (a + b);
+        (relbw_G(mid, kappa) < target ? a : b) = mid;
+    }
+    return 0.5L * (a + b);
+}
+
+// Fills t->relbw_* when a table can be offered: narrow resonance (the solver's fast branch), proper limits, and on every
+// level |alpha| = (half the node spacing in G) |P'(z)| / (kappa^2 + 4) <= PS_RELBW_TABLE_ALPHA.
+#define PS_RELBW_TABLE_ALPHA 0.004
+void build_relbw_table(ps_tree* t, const double sc[5], const double lim[4], double lo, double hi) {
+    const long double p = sc[0], q = sc[1], kappa = sc[2];
+    if (!(kappa >= 16.0) || !(hi > lo) || !(lim[3] > 0.0)) return;
+    const long double z_lo = (lo - p) / q, z_hi = (hi - p) / q, k2 = kappa * kappa + 4.0L;
+    const long double g_lo = lim[2], dg = lim[3];  // exactly the doubles the kernel uses
+    auto abs_P1 = [&](long double z) {
+        const long double y = z + kappa;
+        return fabsl(2.0L * (z * (y * y + 1.0L) + y * (z * z + 1.0L)));
+    };
+    for (int mlog = 9; mlog <= 12; ++mlog) {
+        const int M = 1 << mlog;
+        std::vector<double> nodes;
+        int J_side[2] = {0, 0};
+        bool ok = true;
+        for (int side = 0; side < 2 && ok; ++side) {  // 0: u = w (lower half), 1: u = 1 - w (upper half)
+            // number of levels: the last one (uniform down to w = 0) must resolve the end of the range
+            const long double z_end = side ? z_hi : z_lo;
+            int J = 0;
+            while (J < 40 && 0.5L * dg * ldexpl(1.0L, -(J + 1) - mlog) * abs_P1(z_end) / k2 > PS_RELBW_TABLE_ALPHA) ++J;
+            if (J >= 40) { ok = false; break; }
+            J_side[side] = J;
+            long double z = side ? 0.0L : 0.0L;  // Newton start; the first node of either half is u = 1/2
+            for (int j = 0; j <= J && ok; ++j) {
+                const bool last = j == J;
+                const long double edge = ldexpl(1.0L, last ? -(J + 1) : -(j + 1));          // w of node 0
+                const long double width = ldexpl(1.0L, last ? -(J + 1) : -(j + 2));
+                const long double half_h = 0.5L * dg * width / M;
+                for (int i = 0; i <= M; ++i) {
+                    const long double w = edge - width * i / M;
+                    const long double u = side ? 1.0L - w : w;
+                    z = relbw_root(g_lo + u * dg, kappa, z_lo, z_hi, z);
+                    if (half_h * abs_P1(z) / k2 > PS_RELBW_TABLE_ALPHA) { ok = false; break; }
+                    nodes.push_back((double)z);
+                }
+            }
+        }
+        if (ok) {
+            t->relbw_nodes.swap(nodes);
+            t->relbw_mlog = mlog;
+            t->relbw_J_lo = J_side[0];
+            t->relbw_J_hi = J_side[1];
+            return;
+        }
+    }
+}
+
+}  // namespace
+
 extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tree** out) {
     if (!nodes || !out || n_nodes < 3) return fail(PS_E_INVALID, "a decay tree needs a top particle and at least 2 children");
     if (n_nodes - 1 > PS_MAX_SLOTS) return fail(PS_E_INVALID, "decay tree has more than %d particles", PS_MAX_SLOTS);
@@ -346,6 +433,7 @@ extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tre
             t->base.lim_slot1 = s1;
             host_sampler_limits(nodes[c].kind, nodes[c].mass, nodes[c].width, sc, t->min_mass[c],
                                 nodes[t->top].mass - fs, t->base.lim);
+            if (nodes[c].kind == PS_MASS_RELBW) build_relbw_table(t, sc, t->base.lim, t->min_mass[c], nodes[t->top].mass - fs);
         }
     }
     t->signature = emit_signature(*t, t->top);
@@ -371,7 +459,19 @@ extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tre
     return 0;
 }
 
-extern "C" void ps_tree_destroy(ps_tree* tree) { delete tree; }
+extern "C" void ps_tree_destroy(ps_tree* tree) {
+    if (!tree) return;
+    if (!tree->relbw_dev.empty()) {  // device copies of the relBW node table
+        int cur = 0;
+        const bool have = cudaGetDevice(&cur) == cudaSuccess;
+        for (auto& kv : tree->relbw_dev) {
+            if (cudaSetDevice(kv.first) == cudaSuccess) cudaFree(kv.second);
+        }
+        if (have) cudaSetDevice(cur);
+        (void)cudaGetLastError();
+    }
+    delete tree;
+}
 extern "C" int32_t ps_tree_n_particles(const ps_tree* t) { return t ? t->n_particles : 0; }
 extern "C" int32_t ps_tree_slot(const ps_tree* t, int32_t node) { return (t && node >= 0 && node < t->n_nodes) ? t->slot[node] : -1; }
 extern "C" int32_t ps_tree_n_draws(const ps_tree* t) { return t ? t->n_draws : 0; }
@@ -380,6 +480,7 @@ extern "C" int32_t ps_tree_user_column(const ps_tree* t, int32_t node) { return 
 extern "C" double ps_tree_min_mass(const ps_tree* t, int32_t node) { return (t && node >= 0 && node < t->n_nodes) ? t->min_mass[node] : NAN; }
 extern "C" double ps_tree_w_max(const ps_tree* t) { return t ? t->w_max : NAN; }
 extern "C" const char* ps_tree_signature(const ps_tree* t) { return t ? t->signature.c_str() : ""; }
+extern "C" int32_t ps_tree_relbw_nodes(const ps_tree* t) { return t ? (int32_t)t->relbw_nodes.size() : 0; }
 extern "C" const char* ps_last_error(void) { return g_error.c_str(); }
 extern "C" int32_t ps_abi_version(void) { return PS_ABI_VERSION; }
 extern "C" int64_t ps_launch_count(void) { return g_launches.load(); }
@@ -709,6 +810,22 @@ int fill_params(const ps_tree* t, PsParams& p, uint64_t seed, uint64_t first_eve
     p.err_flag = err_flag;
     p.normalize = (flags & PS_GEN_NORMALIZE) ? 1 : 0;
     p.tiles_per_cta = 0;
+    p.relbw_tab = nullptr;
+    if (!t->relbw_nodes.empty() && !boost_to && n_events > 0) {  // the limits are event independent at rest only
+        int dev = 0;
+        PS_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(t->relbw_mu);
+        double*& d = t->relbw_dev[dev];
+        if (!d) {  // first launch of this tree on this device (not inside a stream capture: warm up first, as for NVRTC)
+            const size_t bytes = t->relbw_nodes.size() * sizeof(double);
+            PS_CUDA(cudaMalloc(&d, bytes));
+            PS_CUDA(cudaMemcpy(d, t->relbw_nodes.data(), bytes, cudaMemcpyHostToDevice));
+        }
+        p.relbw_tab = d;
+        p.relbw_mlog = t->relbw_mlog;
+        p.relbw_J_lo = t->relbw_J_lo;
+        p.relbw_J_hi = t->relbw_J_hi;
+    }
     return 0;
 }
 

@@ -371,7 +371,11 @@ __device__ __forceinline__ void assign_mass_one(C& c, const PsParams& prm, long 
         } else {
             const double u = c.template next<Node::ucol + Node::sampled_before(J)>();
             constexpr bool CONST_LIM = TOP_AT_REST && Node::nonfixed_before(J) == 0;
-            mass = sample_mass<CONST_LIM>(Child::kind, sampler_const(prm, s1), prm.lim, prm.min_mass[s1], max_mass, u);
+            if (CONST_LIM && Child::kind == PS_KIND_RELBW && prm.relbw_tab)
+                mass = sample_relbw_table(sampler_const(prm, s1), prm.lim, prm.relbw_tab, prm.relbw_mlog, prm.relbw_J_lo,
+                                          prm.relbw_J_hi, prm.min_mass[s1], max_mass, u);
+            else
+                mass = sample_mass<CONST_LIM>(Child::kind, sampler_const(prm, s1), prm.lim, prm.min_mass[s1], max_mass, u);
         }
         max_mass = max_mass - mass;  // phasespace.py:352
         m[J] = mass;

@@ -47,6 +47,13 @@ typedef struct PsParams {
     int lim_pad_;
     double lim[4];
 
+    /* The same resonance when it is a relativistic Breit-Wigner: nodes of its inverse CDF (ps_samplers.cuh
+     * sample_relbw_table; built by ps_tree_create, one device copy per GPU).  relbw_tab = NULL: the iterative solver.
+     * Layout: lower half of the uniform (u < 1/2: w = u) then upper half (w = 1 - u); per half J+1 dyadic levels in w
+     * (level j < J: w in [2^-(j+2), 2^-(j+1)), level J: w in [0, 2^-(J+1))), per level M+1 nodes uniform in w. */
+    const double* relbw_tab;
+    int relbw_mlog, relbw_J_lo, relbw_J_hi, relbw_pad_; /* M = 2^relbw_mlog */
+
     double wmax_const;     /* event-independent maximum weight (rest frame, fixed leaf masses) */
     double inv_wmax_const; /* its reciprocal */
 

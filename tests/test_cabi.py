@@ -195,3 +195,31 @@ def test_user_mass_columns_follow_slot_order():
     assert (cols["R1"], cols["R3"], cols["R2"]) == (0, 1, 2) and cols["a"] == -1
     assert np.isnan(_lib.lib.ps_tree_w_max(h))  # R3 is a resonant leaf: w_max depends on the event
     _lib.lib.ps_tree_destroy(h)
+
+
+def test_relbw_node_table_is_offered_where_it_applies():
+    """ps_tree_create builds the inverse-CDF node table (ps_samplers.cuh sample_relbw_table) for a narrow relativistic
+    Breit-Wigner whose limits are event independent -- the first non-fixed child of the top particle -- and for nothing else."""
+    from phasespace_b200 import GenParticle
+    from phasespace_b200.fromdecay import mass_functions as mf
+
+    def kstar_gamma(factory, mass=895.81, width=47.4):
+        return GenParticle("B0", 5279.58).set_children(
+            GenParticle("K*0", factory(mass, width)).set_children(GenParticle("K+", 493.677), GenParticle("pi-", 139.57018)),
+            GenParticle("gamma", 0.0))
+
+    nodes = lambda tree: _lib.lib.ps_tree_relbw_nodes(tree.compile().handle)  # noqa: E731
+    assert nodes(kstar_gamma(mf.relativistic_breitwigner_factory)) > 1000
+    assert nodes(kstar_gamma(mf.relativistic_breitwigner_factory, 1864.84, 3e-6)) > 1000   # a D0 with its physical width
+    assert nodes(kstar_gamma(mf.breitwigner_factory)) == 0 and nodes(kstar_gamma(mf.gauss_factory)) == 0
+    assert nodes(kstar_gamma(mf.relativistic_breitwigner_factory, 775.0, 400.0)) == 0      # broad: kappa < 16, generic solver
+    # a resonance below a resonance has per-event limits: only the first one gets a table (one table per tree)
+    k1 = GenParticle("B+", 5279.58).set_children(
+        GenParticle("K1+", mf.relativistic_breitwigner_factory(1272.0, 90.0)).set_children(
+            GenParticle("K*0", mf.relativistic_breitwigner_factory(895.81, 47.4)).set_children(
+                GenParticle("K+", 493.677), GenParticle("pi-", 139.57018)), GenParticle("pi+", 139.57018)),
+        GenParticle("gamma", 0.0))
+    assert nodes(k1) > 1000
+    from phasespace_b200 import nbody_decay
+
+    assert nodes(nbody_decay(5279.58, [139.57018] * 3)) == 0
