@@ -955,10 +955,12 @@ __device__ __forceinline__ void event_w_max(const C& c, const PsParams& prm, dou
 
 // ------------------------------------------------------------------ stores (store_row / load_row: see above the top-down path)
 // Per-event inputs (the boost_to row, the event index of the regeneration pass) are the only long-latency loads of the
-// loop, and nothing of an event can start before they return: each thread prefetches the input of its NEXT event into L1
-// while it computes the current one.  Config 3 (four bodies + per-event boost_to): 3.58 -> 3.23 ms per 1e8 events.
+// loop, and nothing of an event can start before they return.  PS_PREFETCH_BOOST = 1: each thread prefetches the input of
+// its NEXT event into L1 while it computes the current one (config 3, four bodies + per-event boost_to: 3.58 -> 3.23 ms
+// per 1e8 events); = 2 (generating kernel): the next boost_to row is loaded into registers during the current event, a
+// software pipeline one event deep (3.22 -> 3.09 ms; eight registers, no spills at the 128-register cap).
 #ifndef PS_PREFETCH_BOOST
-#define PS_PREFETCH_BOOST 1
+#define PS_PREFETCH_BOOST 2
 #endif
 __device__ __forceinline__ void prefetch_row(const double* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -1047,6 +1049,13 @@ __device__ __forceinline__ void genbod_body_impl(const PsParams& prm) {
     long long tile = CHUNKED ? (long long)blockIdx.x * prm.tiles_per_cta : (long long)blockIdx.x;
     const long long tile_end = CHUNKED ? (tile + prm.tiles_per_cta < n_tiles ? tile + prm.tiles_per_cta : n_tiles) : n_tiles;
     const long long tile_step = CHUNKED ? 1 : (long long)gridDim.x;
+#if PS_PREFETCH_BOOST == 2
+    double nbx = 0.0, nby = 0.0, nbz = 0.0, nbe = 0.0;
+    if constexpr (BOOST) {
+        const long long i0 = tile * PS_BLOCK + threadIdx.x;
+        if (tile < tile_end && i0 < n) load_row(prm.boost_to + i0 * prm.boost_stride, nbx, nby, nbz, nbe);
+    }
+#endif
     for (; tile < tile_end; tile += tile_step) {
         {
         const long long i = tile * PS_BLOCK + threadIdx.x;
@@ -1072,12 +1081,19 @@ __device__ __forceinline__ void genbod_body_impl(const PsParams& prm) {
             c.out_stride = prm.particle_stride;
             double bx = 0.0, by = 0.0, bz = 0.0, be = 0.0;
             if constexpr (BOOST) {
+#if PS_PREFETCH_BOOST == 2
+                // software pipeline in registers: this event's row was loaded during the previous event
+                bx = nbx, by = nby, bz = nbz, be = nbe;
+                const long long i_next = i + tile_step * PS_BLOCK;
+                if (i_next < n) load_row(prm.boost_to + i_next * prm.boost_stride, nbx, nby, nbz, nbe);
+#else
                 load_row(prm.boost_to + i * prm.boost_stride, bx, by, bz, be);
 #if PS_PREFETCH_BOOST
                 // the row of this thread's NEXT event, into L1 while this event is computed: the load above is the only
                 // long-latency instruction of the loop and nothing can start before it returns
                 const long long i_next = i + tile_step * PS_BLOCK;
                 if (i_next < n) prefetch_row(prm.boost_to + i_next * prm.boost_stride);
+#endif
 #endif
             }
             const double w = gen_node<Tree, !BOOST>(c, prm, i, bx, by, bz, be);
