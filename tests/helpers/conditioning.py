@@ -12,8 +12,10 @@ error eps * gamma^2 (gamma = E / m in the output frame) to its a.  So two correc
 and no better.  Two more terms of the same kind:
 
 * a resonance mass sampled in the kernel comes out of a different inverse-CDF algorithm than the oracle's (CUDA
-  normcdfinv / a series inversion of the relativistic Breit-Wigner CDF against scipy and libm); the two masses agree to
-  ``MASS_NOISE`` of the mass window (tests/test_samplers_gpu.py), and that difference is amplified by the same A;
+  normcdfinv / a table of long-double nodes and a series for the relativistic Breit-Wigner, against scipy and libm); the
+  two masses agree to ``MASS_NOISE`` in the bulk (tests/test_samplers_gpu.py), in the far tails only to what an fp64
+  evaluation of the CDF allows there (``sampler_noise``: dx = dG / G'(x), the density G' vanishes), and that
+  difference is amplified by the same A;
 * the reference boosts with gamma = 1 / sqrt(1 - beta^2) (kinematics.py:141), which itself loses eps * gamma^2 for a fast
   subsystem (1 - beta^2 cancels); the kernel's fast variant boosts with gamma = E / M and is closer to the exact result
   than the reference, so boosted 4-VECTORS (not the weights, which are frame independent) differ by the reference's
@@ -76,6 +78,42 @@ def amplification(desc, particles, boost=None, with_boosts=False):
     return (total, boosts) if with_boosts else total
 
 
+def sampler_noise(desc, particles):
+    """Relative noise of the sampled resonance masses that no fp64 inverse CDF can avoid, per event, summed over the
+    sampled resonances of the tree: the CDF value is known to ~4 eps (a sum of arctangents of order pi), and the inverse
+    maps that to dx = dG / G'(x), which explodes in the far tails where the density G' vanishes.
+
+        relbw:  G'(z) = (kappa^2 + 4) / ((z^2 + 1)((z + kappa)^2 + 1)) per unit of z = (x - p) / q
+        bw:     x = m + w tan(t):  dx = w (1 + z^2) dt
+
+    (The truncated normal keeps its precise tail by construction -- the kernel and the oracle both work in the tail
+    nearest to the lower limit -- and is covered by MASS_NOISE.)  The mass of each resonance is read off its reference
+    4-vector."""
+    n_events = next(iter(particles.values())).shape[0]
+    noise = np.zeros(n_events)
+
+    def walk(d):
+        name, mass, kind, width, children = d
+        if kind in ("relbw", "bw") and name in particles:
+            x = np.maximum(_mass(particles[name]), 1e-300)
+            if kind == "relbw":
+                a, b = mass * mass, mass * width
+                rho = np.sqrt(a * a + b * b)
+                p = np.sqrt(0.5 * (rho + a))
+                q = b / (2.0 * p)
+                kappa = 2.0 * p / q
+                z = (x - p) / q
+                noise[:] += 4.0 * EPS * (z * z + 1.0) * ((z + kappa) ** 2 + 1.0) / (kappa * kappa + 4.0) * q / x
+            else:
+                z = (x - mass) / width
+                noise[:] += 4.0 * EPS * (z * z + 1.0) * width / x
+        for c in children:
+            walk(c)
+
+    walk(desc)
+    return noise
+
+
 def has_sampled_resonance(desc):
     return desc[2] in ("gauss", "bw", "relbw") or any(has_sampled_resonance(c) for c in desc[4])
 
@@ -92,6 +130,8 @@ def event_bounds(desc, particles, boost=None, tol=1e-12, c_amp=8.0):
     mass at rest) for the 4-vectors."""
     amp, boosts = amplification(desc, particles, boost, with_boosts=True)
     unit = max(c_amp * EPS, MASS_NOISE if has_sampled_resonance(desc) else 0.0)
+    if has_sampled_resonance(desc):  # plus what the inverse CDF's conditioning adds for this event's own masses
+        unit = unit + c_amp * sampler_noise(desc, particles)
     w_bound = np.maximum(tol, unit * amp)
     v_bound = np.maximum(tol, unit * amp + c_amp * EPS * boosts)
     return amp, w_bound, v_bound

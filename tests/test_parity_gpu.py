@@ -333,3 +333,29 @@ def test_edge_trees(name):
     largest tree the parameter block holds, a depth-five chain through all three samplers, a decay at threshold."""
     desc, n, tol = _EDGE_TREES[name]
     _compare(desc, n, exact=False, use_rng=True, tol=tol)
+
+
+_RELBW_TABLE_CASES = {
+    # (top mass, resonance mass, width, daughters, third particle): all have event-independent limits -> node table
+    "kstar_like": (5279.58, 895.81, 47.4, (493.677, 139.57018), 0.0),
+    "narrow_1e-5": (5279.58, 1019.461, 0.0102, (493.677, 493.677), 139.57018),
+    "d0_physical_width": (2010.26, 1864.84, 1.6e-9 * 1864.84, (493.677, 139.57018), 139.57018),
+    "upper_limit_100_widths_per_gev": (50000.0, 895.81, 47.4, (493.677, 139.57018), 0.0),
+    "kappa_20": (5279.58, 775.26, 155.0, (139.57018, 139.57018), 139.57018),
+    "window_cuts_the_peak": (1500.0, 895.81, 47.4, (493.677, 139.57018), 620.0),
+}
+
+
+@pytest.mark.parametrize("name", list(_RELBW_TABLE_CASES))
+def test_relbw_node_table_against_the_oracle(name):
+    """The tabulated relativistic Breit-Wigner (event-independent limits: ps_samplers.cuh sample_relbw_table) against the
+    oracle's inverse CDF fed the same uniforms, through the whole generator: weights and 4-vectors within the per-event
+    bounds, for narrow and broad resonances, far upper limits and a window that cuts into the peak."""
+    import phasespace_b200 as ps
+    from phasespace_b200 import _lib
+
+    top, m, w, (d1, d2), third = _RELBW_TABLE_CASES[name]
+    desc = ("X", top, "fixed", 0.0, [("R", m, "relbw", w, [_leaf("a", d1), _leaf("b", d2)]), _leaf("c", third)])
+    assert _lib.lib.ps_tree_relbw_nodes(D.to_gen(desc).compile().handle) > 0
+    _compare(desc, 20000, exact=False, use_rng=True, seed=41)
+    _compare(desc, 5000, exact=True, use_rng=False, seed=42, normalize=False)
