@@ -79,6 +79,15 @@ const char* ps_tree_signature(const ps_tree* tree);
  * event (the first resonance below a top particle at rest), 0 if the tree has none: with a table that resonance is sampled
  * without transcendental functions (ps_samplers.cuh sample_relbw_table; mass_functions.py:70-102). */
 int32_t ps_tree_relbw_nodes(const ps_tree* tree);
+/* Size in doubles of the inverse-CDF node table of the tree, whichever sampler it serves -- the relativistic Breit-Wigner
+ * above (one double per node) or a truncated normal (gauss_factory, mass_functions.py:16-40, and the tfp TruncatedNormal of
+ * tests/helpers/decays.py:26-37: two doubles per node, ps_samplers.cuh sample_gauss_table) -- 0 if it has none. */
+int32_t ps_tree_node_table_size(const ps_tree* tree);
+/* Diagnostic copy of that table (host memory; tests/test_cabi.py checks the nodes against a multi-precision inverse CDF):
+ * returns its size in doubles and copies min(size, capacity) of them to `out` (may be NULL); meta = {mass kind it serves
+ * or -1, log2 of the nodes per level M, levels - 1 of the lower half, of the upper half} (layout: ps_params.h), *w_min =
+ * distance from an end of the uniform's range below which the kernel leaves a draw to the library inverse. */
+int32_t ps_tree_node_table(const ps_tree* tree, double* out, int32_t capacity, int32_t* meta, double* w_min);
 int32_t ps_tree_is_aot(const ps_tree* tree, int32_t with_boost, int32_t with_debug_uniforms, uint32_t flags);
 
 /* Replaces GenParticle.generate / _recursive_generate / _generate / _generate_part2

@@ -104,12 +104,14 @@ struct ps_tree {
     // not pay for a mutex and a map lookup keyed on a hundred-character string every time
     mutable std::atomic<const void*> kernel_cache[3][2][2][2] = {};
     mutable std::atomic<int> blocks_per_sm_cache[3][2][2][2] = {};
-    // nodes of the inverse CDF of a relativistic Breit-Wigner with event-independent limits (PsParams::relbw_tab): built
-    // once on the host, copied to each device at the first launch there
-    std::vector<double> relbw_nodes;
-    int relbw_mlog = 0, relbw_J_lo = 0, relbw_J_hi = 0;
-    mutable std::mutex relbw_mu;
-    mutable std::map<int, double*> relbw_dev;
+    // nodes of the inverse CDF of a relativistic Breit-Wigner or a truncated normal with event-independent limits
+    // (PsParams::node_tab): built once on the host, copied to each device at the first launch there
+    std::vector<double> tab_nodes;
+    int tab_mlog = 0, tab_J_lo = 0, tab_J_hi = 0;
+    double tab_wmin = 0.0;
+    int tab_kind = -1;  // PS_MASS_RELBW or PS_MASS_GAUSS when tab_nodes is not empty
+    mutable std::mutex tab_mu;
+    mutable std::map<int, double*> tab_dev;
     mutable std::atomic<unsigned long long> one_cta_ready[2][2] = {};  // [dbg][exact]: devices (bit mask) on which the shared-memory attribute is set (pick_grid)
 };
 
@@ -315,10 +317,131 @@ void build_relbw_table(ps_tree* t, const double sc[5], const double lim[4], doub
             }
         }
         if (ok) {
-            t->relbw_nodes.swap(nodes);
-            t->relbw_mlog = mlog;
-            t->relbw_J_lo = J_side[0];
-            t->relbw_J_hi = J_side[1];
+            t->tab_nodes.swap(nodes);
+            t->tab_mlog = mlog;
+            t->tab_J_lo = J_side[0];
+            t->tab_J_hi = J_side[1];
+            t->tab_kind = PS_MASS_RELBW;
+            return;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- truncated-normal node table
+// ps_samplers.cuh sample_gauss_table: z_k = Phi^-1(Phi(a) + u_k (Phi(b) - Phi(a))) and 1 / phi(z_k) at the same nodes u_k,
+// a = (lo - m) / w, b = (hi - m) / w.  Every probability is carried as a LOWER-tail or an UPPER-tail value, whichever is
+// the smaller, so that nothing cancels: the table is accurate to the long double's 64 bits even where the fp64 expression
+// Phi(a) + u dPhi of the library path has run out of digits (targets next to 1).
+const long double PS_SQRT1_2L = 0.707106781186547524400844362104849039L;
+const long double PS_SQRT_2PIL = 2.506628274631000502415765284811045253L;
+
+long double norm_lower(long double z) { return 0.5L * erfcl(-z * PS_SQRT1_2L); }  // Phi(z); Phi(-z) is the upper tail
+
+// z with Phi(z) = P for 0 < P <= 1/2: Newton on log Phi (concave and increasing: monotone convergence from the left,
+// and from the right after one step), started from a neighbouring node.
+long double norm_inv_lower(long double P, long double z) {
+    if (!(P > 0.0L)) return -HUGE_VALL;
+    if (!(z < 0.5L)) z = 0.0L;
+    for (int it = 0; it < 200; ++it) {
+        const long double F = norm_lower(z);
+        const long double phi = expl(-0.5L * z * z) / PS_SQRT_2PIL;
+        if (!(F > 0.0L) || !(phi > 0.0L)) { z *= 0.5L; continue; }  // started beyond the long double's range
+        long double step = F / phi * logl(F / P);
+        if (step > 4.0L) step = 4.0L;
+        if (step < -4.0L) step = -4.0L;
+        z -= step;
+        // quadratic convergence: a step of 1e-9 leaves an error of ~|z| step^2 / 2, below the 64-bit floor
+        if (fabsl(step) <= 1e-9L * (1.0L + fabsl(z))) break;
+    }
+    return z;
+}
+
+// Fills t->tab_* when a table can be offered: the seventh-order term of the inverse-function series stays below
+// PS_GAUSS_TABLE_ERR (absolute, in z) at half a node spacing from every node that the kernel may use.
+#define PS_GAUSS_TABLE_ERR 2e-16L
+#define PS_GAUSS_TABLE_MAX_J 50 /* level 50 is w < 2^-51: below the resolution of the generator's own uniforms */
+void build_gauss_table(ps_tree* t, double mass, double width, const double lim[4], double lo, double hi) {
+    if (!(hi > lo) || !(lim[1] > 0.0) || !(width > 0.0)) return;
+    const long double a = ((long double)lo - mass) / width, b = ((long double)hi - mass) / width;
+    const long double P_a = norm_lower(a), Q_a = norm_lower(-a), P_b = norm_lower(b), Q_b = norm_lower(-b);
+    // Phi(b) - Phi(a) without cancellation
+    const long double dP = (a <= 0.0L && b >= 0.0L) ? (1.0L - P_a - Q_b) : (b < 0.0L ? P_b - P_a : Q_a - Q_b);
+    if (!(dP > 0.0L)) return;
+    // (z, 1/phi) of the node at distance w from the lower (side 0) or upper (side 1) end of the range, in units of u
+    auto node = [&](int side, long double w, long double z_start, long double& z, long double& r) {
+        const long double P = side ? P_b - w * dP : P_a + w * dP;  // lower-tail probability of the target
+        const long double Q = side ? Q_b + w * dP : Q_a - w * dP;  // upper-tail probability
+        if (P <= Q) z = norm_inv_lower(P, z_start);
+        else z = -norm_inv_lower(Q, -z_start);
+        r = PS_SQRT_2PIL * expl(0.5L * z * z);
+    };
+    auto series_err = [](long double z, long double d) {  // the seventh-order term of the series in sample_gauss_table
+        const long double z2 = z * z, d2 = d * d;
+        return (127.0L + z2 * (1740.0L + z2 * (2556.0L + z2 * 720.0L))) / 5040.0L * fabsl(d) * d2 * d2 * d2;
+    };
+    for (int mlog = 6; mlog <= 12; ++mlog) {
+        const int M = 1 << mlog;
+        std::vector<double> nodes;
+        int J_side[2] = {0, 0};
+        long double wmin = 0.0L;
+        bool ok = true;
+        for (int side = 0; side < 2 && ok; ++side) {
+            // the last level is uniform down to w = 0: it must be so short that its end node (z = a or b) serves all of
+            // it.  Where that end lies beyond the reach of fp64 (Phi = 0 or 1: z -> infinity as w -> 0) no level does; the
+            // levels then go down to the generator's resolution and the last one is left to the library path (tab_wmin).
+            int J = 0;
+            bool regular_end = false;
+            long double z_end, r_end;
+            node(side, 0.0L, 0.0L, z_end, r_end);
+            if (std::isfinite((double)z_end) && std::isfinite((double)r_end)) {
+                for (; J < PS_GAUSS_TABLE_MAX_J; ++J) {
+                    const long double half_h = 0.5L * dP * ldexpl(1.0L, -(J + 1) - mlog);
+                    if (series_err(z_end, half_h * r_end) <= PS_GAUSS_TABLE_ERR) { regular_end = true; break; }
+                }
+            }
+            if (!regular_end) {
+                J = PS_GAUSS_TABLE_MAX_J;
+                wmin = std::max(wmin, ldexpl(1.0L, -(J + 1)));
+            }
+            J_side[side] = J;
+            long double z = 0.0L, r = 0.0L, w_prev = 0.5L;
+            bool have_prev = false;
+            for (int j = 0; j <= J && ok; ++j) {
+                const bool last = j == J;
+                const long double edge = ldexpl(1.0L, last ? -(J + 1) : -(j + 1));  // w of node 0
+                const long double lw = ldexpl(1.0L, last ? -(J + 1) : -(j + 2));    // width of the level in w
+                const long double half_h = 0.5L * dP * lw / M;
+                for (int i = 0; i <= M; ++i) {
+                    const long double w = edge - lw * i / M;
+                    if (last && !regular_end) {  // never read (tab_wmin)
+                        nodes.push_back(side ? 1e300 : -1e300);
+                        nodes.push_back(0.0);
+                        continue;
+                    }
+                    // Newton start: the kernel's own series from the previous node (one Newton step then confirms it)
+                    long double z0 = z;
+                    if (have_prev) {
+                        const long double d = (side ? w_prev - w : w - w_prev) * dP * r, z2 = z * z;
+                        z0 = z + d * (1.0L + d * (0.5L * z + d * ((2.0L * z2 + 1.0L) / 6.0L + d * (z * (6.0L * z2 + 7.0L) / 24.0L +
+                                 d * ((z2 * (24.0L * z2 + 46.0L) + 7.0L) / 120.0L)))));
+                        if (!std::isfinite((double)z0)) z0 = z;
+                    }
+                    node(side, w, z0, z, r);
+                    w_prev = w;
+                    have_prev = true;
+                    if (!(series_err(z, half_h * r) <= PS_GAUSS_TABLE_ERR)) { ok = false; break; }
+                    nodes.push_back((double)z);
+                    nodes.push_back((double)r);
+                }
+            }
+        }
+        if (ok) {
+            t->tab_nodes.swap(nodes);
+            t->tab_mlog = mlog;
+            t->tab_J_lo = J_side[0];
+            t->tab_J_hi = J_side[1];
+            t->tab_wmin = (double)wmin;
+            t->tab_kind = PS_MASS_GAUSS;
             return;
         }
     }
@@ -433,7 +556,13 @@ extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tre
             t->base.lim_slot1 = s1;
             host_sampler_limits(nodes[c].kind, nodes[c].mass, nodes[c].width, sc, t->min_mass[c],
                                 nodes[t->top].mass - fs, t->base.lim);
-            if (nodes[c].kind == PS_MASS_RELBW) build_relbw_table(t, sc, t->base.lim, t->min_mass[c], nodes[t->top].mass - fs);
+            // PS_B200_NO_NODE_TABLES=1 (A/B measurements): sample with the solver / library inverse instead
+            const char* no_tab = getenv("PS_B200_NO_NODE_TABLES");
+            const bool tables = !(no_tab && *no_tab && *no_tab != '0');
+            if (tables && nodes[c].kind == PS_MASS_RELBW)
+                build_relbw_table(t, sc, t->base.lim, t->min_mass[c], nodes[t->top].mass - fs);
+            if (tables && nodes[c].kind == PS_MASS_GAUSS)
+                build_gauss_table(t, nodes[c].mass, nodes[c].width, t->base.lim, t->min_mass[c], nodes[t->top].mass - fs);
         }
     }
     t->signature = emit_signature(*t, t->top);
@@ -461,10 +590,10 @@ extern "C" int ps_tree_create(const ps_node_desc* nodes, int32_t n_nodes, ps_tre
 
 extern "C" void ps_tree_destroy(ps_tree* tree) {
     if (!tree) return;
-    if (!tree->relbw_dev.empty()) {  // device copies of the relBW node table
+    if (!tree->tab_dev.empty()) {  // device copies of the node table
         int cur = 0;
         const bool have = cudaGetDevice(&cur) == cudaSuccess;
-        for (auto& kv : tree->relbw_dev) {
+        for (auto& kv : tree->tab_dev) {
             if (cudaSetDevice(kv.first) == cudaSuccess) cudaFree(kv.second);
         }
         if (have) cudaSetDevice(cur);
@@ -480,7 +609,23 @@ extern "C" int32_t ps_tree_user_column(const ps_tree* t, int32_t node) { return 
 extern "C" double ps_tree_min_mass(const ps_tree* t, int32_t node) { return (t && node >= 0 && node < t->n_nodes) ? t->min_mass[node] : NAN; }
 extern "C" double ps_tree_w_max(const ps_tree* t) { return t ? t->w_max : NAN; }
 extern "C" const char* ps_tree_signature(const ps_tree* t) { return t ? t->signature.c_str() : ""; }
-extern "C" int32_t ps_tree_relbw_nodes(const ps_tree* t) { return t ? (int32_t)t->relbw_nodes.size() : 0; }
+extern "C" int32_t ps_tree_node_table_size(const ps_tree* t) { return t ? (int32_t)t->tab_nodes.size() : 0; }
+extern "C" int32_t ps_tree_node_table(const ps_tree* t, double* out, int32_t capacity, int32_t* meta, double* w_min) {
+    if (!t) return 0;
+    const int32_t n = (int32_t)t->tab_nodes.size();
+    if (meta) {
+        meta[0] = n ? t->tab_kind : -1;
+        meta[1] = t->tab_mlog;
+        meta[2] = t->tab_J_lo;
+        meta[3] = t->tab_J_hi;
+    }
+    if (w_min) *w_min = t->tab_wmin;
+    if (out) memcpy(out, t->tab_nodes.data(), sizeof(double) * (size_t)(n < capacity ? n : (capacity > 0 ? capacity : 0)));
+    return n;
+}
+extern "C" int32_t ps_tree_relbw_nodes(const ps_tree* t) {
+    return t && t->tab_kind == PS_MASS_RELBW ? (int32_t)t->tab_nodes.size() : 0;
+}
 extern "C" const char* ps_last_error(void) { return g_error.c_str(); }
 extern "C" int32_t ps_abi_version(void) { return PS_ABI_VERSION; }
 extern "C" int64_t ps_launch_count(void) { return g_launches.load(); }
@@ -810,21 +955,22 @@ int fill_params(const ps_tree* t, PsParams& p, uint64_t seed, uint64_t first_eve
     p.err_flag = err_flag;
     p.normalize = (flags & PS_GEN_NORMALIZE) ? 1 : 0;
     p.tiles_per_cta = 0;
-    p.relbw_tab = nullptr;
-    if (!t->relbw_nodes.empty() && !boost_to && n_events > 0) {  // the limits are event independent at rest only
+    p.node_tab = nullptr;
+    if (!t->tab_nodes.empty() && !boost_to && n_events > 0) {  // the limits are event independent at rest only
         int dev = 0;
         PS_CUDA(cudaGetDevice(&dev));
-        std::lock_guard<std::mutex> lock(t->relbw_mu);
-        double*& d = t->relbw_dev[dev];
+        std::lock_guard<std::mutex> lock(t->tab_mu);
+        double*& d = t->tab_dev[dev];
         if (!d) {  // first launch of this tree on this device (not inside a stream capture: warm up first, as for NVRTC)
-            const size_t bytes = t->relbw_nodes.size() * sizeof(double);
+            const size_t bytes = t->tab_nodes.size() * sizeof(double);
             PS_CUDA(cudaMalloc(&d, bytes));
-            PS_CUDA(cudaMemcpy(d, t->relbw_nodes.data(), bytes, cudaMemcpyHostToDevice));
+            PS_CUDA(cudaMemcpy(d, t->tab_nodes.data(), bytes, cudaMemcpyHostToDevice));
         }
-        p.relbw_tab = d;
-        p.relbw_mlog = t->relbw_mlog;
-        p.relbw_J_lo = t->relbw_J_lo;
-        p.relbw_J_hi = t->relbw_J_hi;
+        p.node_tab = d;
+        p.tab_mlog = t->tab_mlog;
+        p.tab_J_lo = t->tab_J_lo;
+        p.tab_J_hi = t->tab_J_hi;
+        p.tab_wmin = t->tab_wmin;
     }
     return 0;
 }

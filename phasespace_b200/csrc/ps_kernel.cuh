@@ -371,11 +371,19 @@ __device__ __forceinline__ void assign_mass_one(C& c, const PsParams& prm, long 
         } else {
             const double u = c.template next<Node::ucol + Node::sampled_before(J)>();
             constexpr bool CONST_LIM = TOP_AT_REST && Node::nonfixed_before(J) == 0;
-            if (CONST_LIM && Child::kind == PS_KIND_RELBW && prm.relbw_tab)
-                mass = sample_relbw_table(sampler_const(prm, s1), prm.lim, prm.relbw_tab, prm.relbw_mlog, prm.relbw_J_lo,
-                                          prm.relbw_J_hi, prm.min_mass[s1], max_mass, u);
-            else
+            if (CONST_LIM && Child::kind == PS_KIND_RELBW && prm.node_tab) {
+                mass = sample_relbw_table(sampler_const(prm, s1), prm.lim, prm.node_tab, prm.tab_mlog, prm.tab_J_lo,
+                                          prm.tab_J_hi, prm.min_mass[s1], max_mass, u);
+            } else if (CONST_LIM && Child::kind == PS_KIND_GAUSS && prm.node_tab) {
+                double du, w;
+                const int idx = node_locate(u, prm.tab_mlog, prm.tab_J_lo, prm.tab_J_hi, du, w);
+                if (w >= prm.tab_wmin)
+                    mass = sample_gauss_table(sampler_const(prm, s1), prm.lim, prm.node_tab, idx, du, prm.min_mass[s1], max_mass);
+                else  // next to an end of the range that lies where Phi is 0 or 1 in fp64 (PsParams::tab_wmin)
+                    mass = sample_gauss<CONST_LIM>(sampler_const(prm, s1), prm.lim, prm.min_mass[s1], max_mass, u);
+            } else {
                 mass = sample_mass<CONST_LIM>(Child::kind, sampler_const(prm, s1), prm.lim, prm.min_mass[s1], max_mass, u);
+            }
         }
         max_mass = max_mass - mass;  // phasespace.py:352
         m[J] = mass;

@@ -47,12 +47,16 @@ typedef struct PsParams {
     int lim_pad_;
     double lim[4];
 
-    /* The same resonance when it is a relativistic Breit-Wigner: nodes of its inverse CDF (ps_samplers.cuh
-     * sample_relbw_table; built by ps_tree_create, one device copy per GPU).  relbw_tab = NULL: the iterative solver.
+    /* The same resonance when it is a relativistic Breit-Wigner or a truncated normal: nodes of its inverse CDF
+     * (ps_samplers.cuh sample_relbw_table / sample_gauss_table; built by ps_tree_create, one device copy per GPU).
+     * node_tab = NULL: the iterative solver / library inverse.
      * Layout: lower half of the uniform (u < 1/2: w = u) then upper half (w = 1 - u); per half J+1 dyadic levels in w
-     * (level j < J: w in [2^-(j+2), 2^-(j+1)), level J: w in [0, 2^-(J+1))), per level M+1 nodes uniform in w. */
-    const double* relbw_tab;
-    int relbw_mlog, relbw_J_lo, relbw_J_hi, relbw_pad_; /* M = 2^relbw_mlog */
+     * (level j < J: w in [2^-(j+2), 2^-(j+1)), level J: w in [0, 2^-(J+1))), per level M+1 nodes uniform in w.
+     * A node is one double (RELBW: z) or two (GAUSS: z, 1/phi(z)).  tab_wmin (GAUSS): draws with min(u, 1-u) below it
+     * take the library path (0 unless an end of the range lies where Phi is 0 or 1 in fp64). */
+    const double* node_tab;
+    int tab_mlog, tab_J_lo, tab_J_hi, tab_pad_; /* M = 2^tab_mlog */
+    double tab_wmin;
 
     double wmax_const;     /* event-independent maximum weight (rest frame, fixed leaf masses) */
     double inv_wmax_const; /* its reciprocal */

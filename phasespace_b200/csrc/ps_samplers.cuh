@@ -221,17 +221,19 @@ __device__ __forceinline__ double sample_relbw(const SamplerConst& k, const doub
     return clamp_mass(fma(k.c1, z, k.c0), lo, hi);
 }
 
-// ------------------------------------------------------------------ relativistic Breit-Wigner from a table of nodes
+// ------------------------------------------------------------------ inverse CDFs from a table of nodes
 // Event-independent limits (the first resonance below a top particle at rest, e.g. B -> K* gamma): the target value of the
-// CDF is G_lo + u dG with the same G_lo, dG for every event, so the host can solve G(z_k) = G_lo + u_k dG once for a set of
-// nodes u_k (ps_api.cu build_relbw_table, long double) and the kernel needs no transcendental function at all: it takes
-// the nearest node, knows h = (u - u_k) dG EXACTLY (no evaluation of G), and applies the fourth-order inverse-function
-// series of the solver above around z_k.  The nodes are uniform in w = min(u, 1 - u) within dyadic levels [2^-(j+2), 2^-(j+1)),
-// which puts them where z(u) bends -- the tails; the host checks on every level that the series parameter
-// |alpha| = h |P'(z)| / (kappa^2 + 4) stays below 0.004 (truncation ~ alpha^4 / 100 of the step) or does not offer a table.
-// ~45 instructions (30 fp64, one 8-byte load) instead of ~350 (140 fp64, 12 MUFU).
-__device__ __forceinline__ double sample_relbw_table(const SamplerConst& k, const double* lim, const double* tab, int mlog,
-                                                     int J_lo, int J_hi, double lo, double hi, double u) {
+// CDF is F_lo + u dF with the same F_lo, dF for every event, so the host can solve F(z_k) = F_lo + u_k dF once for a set of
+// nodes u_k (ps_api.cu build_relbw_table / build_gauss_table, long double) and the kernel needs no transcendental function
+// at all: it takes the nearest node, knows h = (u - u_k) dF EXACTLY (no evaluation of F), and applies the fourth-order
+// inverse-function series around z_k.  The nodes are uniform in w = min(u, 1 - u) within dyadic levels
+// [2^-(j+2), 2^-(j+1)), which puts them where z(u) bends -- the tails; the host checks on every level that the truncation
+// error of the series stays below the rounding floor or does not offer a table.
+//
+// Layout (PsParams::node_tab): lower half of the uniform (u < 1/2: w = u) then upper half (w = 1 - u); per half J+1 levels
+// (level j < J: w in [2^-(j+2), 2^-(j+1)), level J: w in [0, 2^-(J+1))), per level M+1 = 2^mlog + 1 nodes, node 0 at the
+// upper edge of the level.  node_locate returns the index of the nearest node and du = u - u_node (exact).
+__device__ __forceinline__ int node_locate(double u, int mlog, int J_lo, int J_hi, double& du, double& w_out) {
     const int M = 1 << mlog;  // nodes per level: M + 1
     const bool upper = u >= 0.5;
     const double w = upper ? 1.0 - u : u;  // exact
@@ -246,8 +248,19 @@ __device__ __forceinline__ double sample_relbw_table(const SamplerConst& k, cons
     const double s = ((last ? 1.0 : 2.0) - x) * __hiloint2double((1023 + mlog) << 20, 0);  // exact: position in the level, 0 .. M
     const int i = __double2int_rn(s);
     const double dw = (s - (double)i) * __hiloint2double((1023 - sh - mlog) << 20, 0);       // w_node - w, exact
-    const double h = (upper ? dw : -dw) * lim[3] * k.c4;       // (u - u_node) dG / (kappa^2 + 4)
-    const double z = __ldg(tab + (upper ? (J_lo + 1) * (M + 1) : 0) + j * (M + 1) + i);
+    du = upper ? dw : -dw;
+    w_out = w;
+    return (upper ? (J_lo + 1) * (M + 1) : 0) + j * (M + 1) + i;
+}
+
+// Relativistic Breit-Wigner: one z per node; the series parameter |alpha| = h |P'(z)| / (kappa^2 + 4) stays below 0.004
+// (truncation ~ alpha^4 / 100 of the step).  ~45 instructions (30 fp64, one 8-byte load) instead of ~350 (140 fp64, 12 MUFU).
+__device__ __forceinline__ double sample_relbw_table(const SamplerConst& k, const double* lim, const double* tab, int mlog,
+                                                     int J_lo, int J_hi, double lo, double hi, double u) {
+    double du, w;
+    const int idx = node_locate(u, mlog, J_lo, J_hi, du, w);
+    const double h = du * lim[3] * k.c4;       // (u - u_node) dG / (kappa^2 + 4)
+    const double z = __ldg(tab + idx);
     const double y = z + k.c2;
     const double A = fma(z, z, 1.0), B = fma(y, y, 1.0);
     const double P1 = 2.0 * fma(z, B, y * A);  // P = A B and its derivatives
@@ -259,6 +272,30 @@ __device__ __forceinline__ double sample_relbw_table(const SamplerConst& k, cons
     const double s4 = fma(al, fma(4.0, be, al2), ga);
     const double corr = fma(s4, 1.0 / 24.0, fma(be + al2, 1.0 / 6.0, fma(al, 0.5, 1.0)));
     return clamp_mass(fma(k.c1, fma(d, corr, z), k.c0), lo, hi);
+}
+
+// Truncated normal: per node z_k = Phi^-1(p_k) and r_k = 1 / phi(z_k) (one 16-byte load).  The derivatives of the inverse
+// are d^n z / dp^n = P_(n-1)(z) r^n with P_0 = 1, P_n = P'_(n-1) + n z P_(n-1), so with d = h r_k
+//     z(p_k + h) = z + d + z d^2/2 + (2 z^2 + 1) d^3/6 + (6 z^3 + 7 z) d^4/24 + (24 z^4 + 46 z^2 + 7) d^5/120
+//                  + (120 z^5 + 326 z^3 + 127 z) d^6/720 + O((720 z^6 + 2556 z^4 + 1740 z^2 + 127) d^7/5040);
+// the host keeps that last term below 2e-16 at every node.  Sixth order rather than fourth because it lets the table be
+// four times smaller (65 or 129 nodes per level): the nodes are read with one divergent load per warp, and with 513 nodes
+// per level nearly every warp had a lane that missed L1 (measured: 2.21 ms per 1e8 K* gamma events, 2.4 with normcdfinv).
+// Draws closer to an end of the range than w_min (only where an end lies so far out that Phi there is 0 or 1 in fp64, and
+// then only u = 0 from the generator's own 51-bit stream) are left to the library path by the caller.
+// ~40 instructions (21 fp64) instead of ~180 (normcdfinv).
+__device__ __forceinline__ double sample_gauss_table(const SamplerConst& k, const double* lim, const double* tab, int idx,
+                                                     double du, double lo, double hi) {
+    const double2 node = __ldg(reinterpret_cast<const double2*>(tab) + idx);
+    const double z = node.x;
+    const double d = du * lim[1] * node.y;     // (u - u_node) (Phi(b) - Phi(a)) / phi(z)
+    const double z2 = z * z;
+    const double c3 = fma(z2, 1.0 / 3.0, 1.0 / 6.0);
+    const double c4 = z * fma(z2, 0.25, 7.0 / 24.0);
+    const double c5 = fma(z2, fma(z2, 0.2, 23.0 / 60.0), 7.0 / 120.0);
+    const double c6 = z * fma(z2, fma(z2, 1.0 / 6.0, 163.0 / 360.0), 127.0 / 720.0);
+    const double corr = fma(d, fma(d, fma(d, fma(d, fma(d, c6, c5), c4), c3), 0.5 * z), 1.0);
+    return clamp_mass(fma(k.w, fma(d, corr, z), k.m), lo, hi);
 }
 
 template <bool CONST_LIM>

@@ -86,14 +86,31 @@ def sampler_noise(desc, particles):
         relbw:  G'(z) = (kappa^2 + 4) / ((z^2 + 1)((z + kappa)^2 + 1)) per unit of z = (x - p) / q
         bw:     x = m + w tan(t):  dx = w (1 + z^2) dt
 
-    (The truncated normal keeps its precise tail by construction -- the kernel and the oracle both work in the tail
-    nearest to the lower limit -- and is covered by MASS_NOISE.)  The mass of each resonance is read off its reference
-    4-vector."""
+        gauss:  the fp64 expression Phi(a) + u (Phi(b) - Phi(a)) (oracle, and the kernel's library path) is rounded on
+                the scale of its own value p: dz = eps p / phi(z).  Kernel and oracle both work in the tail nearest to
+                the lower limit (mirrored when the lower limit lies above the pole: lo = the sum of the fixed masses
+                below the resonance, event independent), where p / phi -> 1 / |z| stays small; towards the OTHER end
+                p -> 1 and the digits run out (z = 5: dz ~ 1e-10).  The kernel's node table for event-independent limits
+                (ps_samplers.cuh sample_gauss_table) does not lose them, the oracle it is compared with does.
+
+    The mass of each resonance is read off its reference 4-vector."""
     n_events = next(iter(particles.values())).shape[0]
     noise = np.zeros(n_events)
 
+    def min_mass(d):  # recurse_stable (phasespace.py:326-333)
+        return sum(c[1] if c[2] == "fixed" else min_mass(c) for c in d[4])
+
     def walk(d):
         name, mass, kind, width, children = d
+        if kind == "gauss" and name in particles:
+            from scipy.special import ndtr
+
+            x = np.maximum(_mass(particles[name]), 1e-300)
+            z = (x - mass) / width
+            if min_mass(d) > mass:
+                z = -z
+            zc = np.minimum(np.abs(z), 37.0) * np.sign(z)
+            noise[:] += 4.0 * EPS * ndtr(zc) * np.sqrt(2.0 * np.pi) * np.exp(0.5 * zc * zc) * width / x
         if kind in ("relbw", "bw") and name in particles:
             x = np.maximum(_mass(particles[name]), 1e-300)
             if kind == "relbw":

@@ -223,3 +223,98 @@ def test_relbw_node_table_is_offered_where_it_applies():
     from phasespace_b200 import nbody_decay
 
     assert nodes(nbody_decay(5279.58, [139.57018] * 3)) == 0
+
+
+def _node_table(tree):
+    handle = tree.compile().handle
+    n = _lib.lib.ps_tree_node_table_size(handle)
+    out = np.zeros(max(n, 1))
+    meta, w_min = (ctypes.c_int32 * 4)(), ctypes.c_double()
+    assert _lib.lib.ps_tree_node_table(handle, out.ctypes.data, n, ctypes.addressof(meta), ctypes.addressof(w_min)) == n
+    return out[:n], list(meta), w_min.value
+
+
+def _locate_node(u, mlog, j_lo, j_hi):
+    """numpy statement of ps_samplers.cuh node_locate: index of the nearest node and u - u_node (exact)."""
+    m_nodes = 1 << mlog
+    upper = u >= 0.5
+    w = np.where(upper, 1.0 - u, u)
+    big_j = np.where(upper, j_hi, j_lo)
+    j = np.where(w > 0, -(np.frexp(w)[1] - 1) - 2, 1 << 20)
+    j = np.maximum(j, 0)
+    last = j >= big_j
+    j = np.where(last, big_j, j)
+    sh = np.where(last, big_j + 1, j + 2)
+    s = np.ldexp(np.where(last, 1.0, 2.0) - np.ldexp(w, sh), mlog)
+    i = np.rint(s).astype(np.int64)
+    dw = np.ldexp(s - i, -sh - mlog)
+    return np.where(upper, (j_lo + 1) * (m_nodes + 1), 0) + j * (m_nodes + 1) + i, np.where(upper, dw, -dw), w
+
+
+@pytest.mark.parametrize("case", [
+    (5279.58, 895.81, 47.4, 493.677, 139.57018, 0.0),     # K*-like: lower limit 5.5 widths below the pole, upper 92 above
+    (1500.0, 895.81, 47.4, 493.677, 139.57018, 620.0),    # window that ends below the pole
+    (5279.58, 895.81, 47.4, 493.677, 493.677, 0.0),       # lower limit above the pole
+    (2010.26, 1864.84, 0.05, 493.677, 139.57018, 139.57018),  # both ends thousands of widths away
+], ids=["kstar", "below_pole", "above_pole", "narrow"])
+def test_gauss_node_table_matches_multiprecision_inverse_cdf(case):
+    """ps_tree_create's table for a truncated normal with event-independent limits (ps_samplers.cuh sample_gauss_table;
+    the sampler of tests/helpers/decays.py:26-37 and mass_functions.py:16-40): the kernel's arithmetic, restated in numpy on
+    the host copy of the table, against a 40-digit inverse CDF, for draws all over [0, 1) and hard against both ends."""
+    import phasespace_b200 as ps
+    from phasespace_b200.fromdecay import mass_functions as mf
+
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    top, m, width, d1, d2, third = case
+    tree = ps.GenParticle("X", top).set_children(
+        ps.GenParticle("R", mf.gauss_factory(m, width)).set_children(ps.GenParticle("a", d1), ps.GenParticle("b", d2)),
+        ps.GenParticle("c", third))
+    tab, (kind, mlog, j_lo, j_hi), w_min = _node_table(tree)
+    assert kind == 1 and tab.size == 2 * ((j_lo + 1) + (j_hi + 1)) * ((1 << mlog) + 1)
+    lo, hi = d1 + d2, top - third
+    a, b = mp.mpf(lo - m) / width, mp.mpf(hi - m) / width
+    p_a, q_a, p_b, q_b = mp.ncdf(a), mp.ncdf(-a), mp.ncdf(b), mp.ncdf(-b)
+    d_p = (1 - p_a - q_b) if a <= 0 <= b else (p_b - p_a if b < 0 else q_a - q_b)
+    rng = np.random.default_rng(5)
+    ends = np.ldexp(rng.random(300) + 0.5, -rng.integers(1, 52, 300))
+    u = np.concatenate([rng.random(1500), ends, 1.0 - ends, [0.0, 0.5, 0.25, 0.75, 2.0 ** -51, 1 - 2.0 ** -51]])
+    u = np.floor(u * 2.0 ** 51) / 2.0 ** 51  # the generator's own grid
+    idx, du, w = _locate_node(u, mlog, j_lo, j_hi)
+    keep = w >= w_min  # closer to an end than w_min: left to the library path by the kernel
+    assert keep.sum() >= u.size - 8 and (w_min == 0.0 or w_min == 2.0 ** -51)
+    z, r = tab[2 * idx], tab[2 * idx + 1]
+    with np.errstate(all="ignore"):
+        d = du * float(d_p) * r
+        z2 = z * z
+        c3, c4 = z2 / 3.0 + 1.0 / 6.0, z * (z2 * 0.25 + 7.0 / 24.0)
+        c5, c6 = z2 * (z2 * 0.2 + 23.0 / 60.0) + 7.0 / 120.0, z * (z2 * (z2 / 6.0 + 163.0 / 360.0) + 127.0 / 720.0)
+        z_new = d * (d * (d * (d * (d * (d * c6 + c5) + c4) + c3) + 0.5 * z) + 1.0) + z
+    for uk, zk in zip(u[keep], z_new[keep]):
+        p_lower, p_upper = p_a + mp.mpf(float(uk)) * d_p, q_b + (1 - mp.mpf(float(uk))) * d_p
+        if p_lower <= p_upper:
+            exact = -mp.sqrt(2) * mp.erfinv(1 - 2 * p_lower) if p_lower > mp.mpf("1e-25") else None
+        else:
+            exact = mp.sqrt(2) * mp.erfinv(1 - 2 * p_upper) if p_upper > mp.mpf("1e-25") else None
+        if exact is None:  # erfinv loses its argument next to 1: compare the probabilities instead
+            got_p = mp.ncdf(mp.mpf(float(zk))) if p_lower <= p_upper else mp.ncdf(-mp.mpf(float(zk)))
+            want_p = min(p_lower, p_upper)
+            assert abs(got_p - want_p) <= 1e-14 * want_p * (1 + zk * zk), (uk, zk)
+        else:
+            assert abs(zk - float(exact)) <= 4 * np.spacing(max(abs(zk), 1.0)), (uk, zk, float(exact))
+
+
+def test_node_tables_are_offered_per_sampler():
+    """Cauchy resonances and trees without a sampled resonance have no table; ps_tree_relbw_nodes counts only its own."""
+    import phasespace_b200 as ps
+    from phasespace_b200.fromdecay import mass_functions as mf
+
+    def chain(factory):
+        return ps.GenParticle("B0", 5279.58).set_children(
+            ps.GenParticle("K*0", factory(895.81, 47.4)).set_children(ps.GenParticle("K+", 493.677), ps.GenParticle("pi-", 139.57018)),
+            ps.GenParticle("gamma", 0.0))
+    size = lambda tree: _lib.lib.ps_tree_node_table_size(tree.compile().handle)  # noqa: E731
+    assert size(chain(mf.gauss_factory)) > 0 and size(chain(mf.relativistic_breitwigner_factory)) > 0
+    assert size(chain(mf.breitwigner_factory)) == 0
+    assert _lib.lib.ps_tree_relbw_nodes(chain(mf.gauss_factory).compile().handle) == 0
+    assert size(ps.nbody_decay(5279.58, [139.57018] * 3)) == 0

@@ -359,3 +359,51 @@ def test_relbw_node_table_against_the_oracle(name):
     assert _lib.lib.ps_tree_relbw_nodes(D.to_gen(desc).compile().handle) > 0
     _compare(desc, 20000, exact=False, use_rng=True, seed=41)
     _compare(desc, 5000, exact=True, use_rng=False, seed=42, normalize=False)
+
+
+_GAUSS_TABLE_CASES = {
+    # (top mass, resonance mass, width, daughters, third particle): event-independent limits -> node table
+    "kstar_like": (5279.58, 895.81, 47.4, (493.677, 139.57018), 0.0),
+    "window_cuts_the_peak": (1500.0, 895.81, 47.4, (493.677, 139.57018), 620.0),
+    "lower_limit_above_the_pole": (5279.58, 895.81, 47.4, (493.677, 493.677), 0.0),
+    "narrow": (5279.58, 1019.461, 4.2, (493.677, 493.677), 139.57018),
+    "both_ends_thousands_of_widths_away": (2010.26, 1864.84, 0.05, (493.677, 139.57018), 139.57018),
+    "broad": (3000.0, 2500.0, 300.0, (139.57018, 139.57018), 139.57018),
+}
+
+
+@pytest.mark.parametrize("name", list(_GAUSS_TABLE_CASES))
+def test_gauss_node_table_against_the_oracle(name):
+    """The tabulated truncated normal (event-independent limits: ps_samplers.cuh sample_gauss_table) against the oracle's
+    inverse CDF (scipy ndtr / ndtri) fed the same uniforms, through the whole generator, for windows around, below and
+    above the pole, narrow and broad widths.  Also with the draws pushed against both ends of [0, 1): the last
+    dyadic levels of the table and, where an end of the mass range lies beyond the reach of fp64, the library path."""
+    from phasespace_b200 import _lib
+
+    top, m, w, (d1, d2), third = _GAUSS_TABLE_CASES[name]
+    desc = ("X", top, "fixed", 0.0, [("R", m, "gauss", w, [_leaf("a", d1), _leaf("b", d2)]), _leaf("c", third)])
+    assert _lib.lib.ps_tree_node_table_size(D.to_gen(desc).compile().handle) > 0
+    _compare(desc, 20000, exact=False, use_rng=True, seed=41)
+    _compare(desc, 5000, exact=True, use_rng=False, seed=42, normalize=False)
+    # debug uniforms with the resonance's draw (column 0) pushed towards 0 and 1, on and off the generator's 51-bit grid.
+    # An end of the mass range that the draws can actually reach is approached only to 2^-37: a resonance mass within
+    # rounding of its limit makes the reference itself fail ("Forbidden decay": the mass it re-derives from the boosted
+    # 4-vector dips below the daughters' sum).  An end beyond the reach of fp64 is approached to the last bit.
+    singular_lo, singular_hi = name == "both_ends_thousands_of_widths_away", name in (
+        "kstar_like", "lower_limit_above_the_pole", "narrow", "both_ends_thousands_of_widths_away")
+    gen, tree = D.to_gen(desc), D.to_oracle(desc)
+    n = 4096
+    draws = uniform_table(43, 0, n, orc.n_draws(tree))
+    k = np.arange(n)
+    lower = k % 2 == 0
+    depth = np.where(lower, 51 if singular_lo else 37, 51 if singular_hi else 37)
+    tiny = np.ldexp(draws[:, 0] + 0.5, -((k // 2) % depth) - 1)
+    draws[:, 0] = np.where(lower, tiny, 1.0 - tiny)
+    if singular_hi:
+        draws[:4, 0] = [1.0 - 2.0 ** -51, 1.0 - 2.0 ** -50, 0.5, 0.25]
+    if singular_lo:
+        draws[4:6, 0] = [2.0 ** -51, 2.0 ** -50]
+    assert draws[:, 0].min() > 0.0 and draws[:, 0].max() < 1.0
+    ref = orc.generate(tree, n, draws)
+    got = gen.generate(n, debug_uniforms=torch.as_tensor(draws), exact=False)
+    _check_against(desc, got, ref, None, f"gauss_table/{name}/ends")
