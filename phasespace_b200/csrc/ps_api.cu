@@ -22,6 +22,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/phasespace_b200.h"
@@ -252,77 +253,158 @@ void host_sampler_limits(int kind, double mass, double width, const double sc[5]
 // G(z) = G_lo + u dG at the nodes u_k once (long double Newton from the neighbouring node, bisection as a safeguard).
 namespace {
 
-long double relbw_G(long double z, long double kappa) {
-    const long double y = z + kappa;
-    return atanl(z) + atanl(y) + logl((y * y + 1.0L) / (z * z + 1.0L)) / kappa;
+// G(z) - G(z_r) without cancellation: differences of arctangents as one atan2, of logarithms as log1p.  In the far tails
+// G is flat to within the resolution of G itself (a D meson with its physical width: G changes by 1e-19, the long double's
+// last bit, over 5e4 units of z at the lower limit), so nodes there are solved relative to the END of the range they
+// approach; the targets w dG (lower half of the uniform) and -w dG (upper half) are exact.  As a side effect u -> 0 and
+// u -> 1 map to the mass limits exactly.  (z, z_r >= -kappa/2 because masses are >= 0, so y = z + kappa >= kappa/2 > 0.)
+long double relbw_dG(long double z, long double zr, long double kappa) {
+    const long double y = z + kappa, yr = zr + kappa, dz = z - zr;
+    const long double ay = dz * (y + yr) / (yr * yr + 1.0L), az = dz * (z + zr) / (zr * zr + 1.0L);
+    long double logs;
+    if (ay > -0.999999L && az > -0.999999L)
+        logs = log1pl(ay) - log1pl(az);
+    else  // a ratio next to zero: the plain form is as good there
+        logs = logl((y * y + 1.0L) / (yr * yr + 1.0L)) - logl((z * z + 1.0L) / (zr * zr + 1.0L));
+    return atan2l(dz, 1.0L + z * zr) + atan2l(dz, 1.0L + y * yr) + logs / kappa;
 }
 
-long double relbw_root(long double target, long double kappa, long double z_lo, long double z_hi, long double z) {
+// z with G(z) - G(z_r) = target: Newton from a close start (the series around the neighbouring node), bisection as a safeguard
+long double relbw_root(long double target, long double zr, long double kappa, long double z_lo, long double z_hi, long double z) {
     const long double k2 = kappa * kappa + 4.0L;
     z = z < z_lo ? z_lo : (z > z_hi ? z_hi : z);
+    long double prev_step = HUGE_VALL;
     for (int it = 0; it < 40; ++it) {
         const long double y = z + kappa;
-        const long double step = (relbw_G(z, kappa) - target) * (z * z + 1.0L) * (y * y + 1.0L) / k2;
+        const long double step = (relbw_dG(z, zr, kappa) - target) * (z * z + 1.0L) * (y * y + 1.0L) / k2;
         long double zn = z - step;
         zn = zn < z_lo ? z_lo : (zn > z_hi ? z_hi : zn);
         // quadratic convergence: a step below 1e-10 leaves an error below 1e-19, the noise floor of the 64-bit mantissa
         if (fabsl(zn - z) <= 1e-10L * (1.0L + fabsl(zn))) return zn;
+        // steps that stopped shrinking below 1e-6: the rounding noise of G itself, amplified by 1 / G' (far tails)
+        if (it >= 2 && fabsl(step) >= 0.5L * fabsl(prev_step) && fabsl(step) <= 1e-6L * (1.0L + fabsl(zn))) return zn;
+        prev_step = step;
         z = zn;
     }
     long double a = z_lo, b = z_hi;  // Newton did not settle (never seen): bisection
     for (int it = 0; it < 200; ++it) {
         const long double mid = 0.5L * (a + b);
-        (relbw_G(mid, kappa) < target ? a : b) = mid;
+        (relbw_dG(mid, zr, kappa) < target ? a : b) = mid;
     }
     return 0.5L * (a + b);
 }
 
-// Fills t->relbw_* when a table can be offered: narrow resonance (the solver's fast branch), proper limits, and on every
-// level |alpha| = (half the node spacing in G) |P'(z)| / (kappa^2 + 4) <= PS_RELBW_TABLE_ALPHA.
+// Fills t->tab_* when a table can be offered: narrow resonance (the solver's fast branch), proper limits, and at every node
+// |alpha| = (half the node spacing in G) |P'(z)| / (kappa^2 + 4) <= PS_RELBW_TABLE_ALPHA.
+//
+// Cost: a tree with a D meson of its physical width (kappa ~ 5e12: 80 levels of 1025 nodes) took 0.5 s, a 21-mode
+// DecayLanguage chain 12 s before its first event.  Now (a) every node starts from the kernel's own fourth-order series around
+// its neighbour, so one Newton step confirms it instead of four or five finding it; (b) the levels are independent and are
+// solved on the host's cores in parallel; (c) |P'| peaks INSIDE the last (uniform) level when the lower limit lies beyond
+// the pole of the second Lorentzian, where the estimate of the level count from the end of the range alone is a few per cent
+// short: a failure there adds a level instead of doubling the nodes of every level (which cannot help, and ended with no
+// table at all after four full attempts).
 #define PS_RELBW_TABLE_ALPHA 0.004
+#define PS_RELBW_TABLE_MAX_J 40
+struct RelbwTableSpec {
+    long double kappa, k2, z_lo, z_hi, g_lo, dg;
+};
+
+// nodes of level j of one side (0: u = w, 1: u = 1 - w) into out[0 .. M]; false if the series parameter is too large somewhere
+bool relbw_table_level(const RelbwTableSpec& s, int side, int j, int J, int mlog, double* out) {
+    const int M = 1 << mlog;
+    const bool last = j == J;
+    const long double edge = ldexpl(1.0L, last ? -(J + 1) : -(j + 1));  // w of node 0
+    const long double width = ldexpl(1.0L, last ? -(J + 1) : -(j + 2));
+    const long double half_h = 0.5L * s.dg * width / M;
+    const long double zr = side ? s.z_hi : s.z_lo;  // the end of the range this half of the uniform approaches
+    long double z = 0.0L, g_prev = 0.0L;
+    for (int i = 0; i <= M; ++i) {
+        const long double w = edge - width * i / M;
+        const long double target = (side ? -w : w) * s.dg;  // G(z) - G(z_r)
+        long double z0;
+        if (i == 0) {  // no neighbour yet: the core is linear in t = atan z
+            const long double t_lo = atanl(s.z_lo), t_hi = atanl(s.z_hi);
+            z0 = tanl(t_lo + (side ? 1.0L - w : w) * (t_hi - t_lo));
+        } else {  // ps_samplers.cuh sample_relbw_table, around the previous node
+            const long double y = z + s.kappa, A = z * z + 1.0L, B = y * y + 1.0L, h = (target - g_prev) / s.k2;
+            const long double P1 = 2.0L * (z * B + y * A), P2 = 8.0L * z * y + 2.0L * (A + B), P3 = 12.0L * (y + z);
+            const long double d = h * A * B, al = h * P1, be = h * P2 * d, ga = h * P3 * d * d;
+            z0 = z + d * (1.0L + al / 2.0L + (be + al * al) / 6.0L + (ga + 4.0L * al * be + al * al * al) / 24.0L);
+            if (!std::isfinite((double)z0)) z0 = z;
+        }
+        z = w == 0.0L ? zr : relbw_root(target, zr, s.kappa, s.z_lo, s.z_hi, z0);
+        g_prev = target;
+        const long double y = z + s.kappa;
+        if (half_h * fabsl(2.0L * (z * (y * y + 1.0L) + y * (z * z + 1.0L))) / s.k2 > PS_RELBW_TABLE_ALPHA) return false;
+        out[i] = (double)z;
+    }
+    return true;
+}
+
 void build_relbw_table(ps_tree* t, const double sc[5], const double lim[4], double lo, double hi) {
     const long double p = sc[0], q = sc[1], kappa = sc[2];
     if (!(kappa >= 16.0) || !(hi > lo) || !(lim[3] > 0.0)) return;
-    const long double z_lo = (lo - p) / q, z_hi = (hi - p) / q, k2 = kappa * kappa + 4.0L;
-    const long double g_lo = lim[2], dg = lim[3];  // exactly the doubles the kernel uses
+    RelbwTableSpec s;
+    s.kappa = kappa, s.k2 = kappa * kappa + 4.0L, s.z_lo = (lo - p) / q, s.z_hi = (hi - p) / q;
+    s.g_lo = lim[2], s.dg = lim[3];  // exactly the doubles the kernel uses
     auto abs_P1 = [&](long double z) {
         const long double y = z + kappa;
         return fabsl(2.0L * (z * (y * y + 1.0L) + y * (z * z + 1.0L)));
     };
+    const bool debug = getenv("PS_B200_DEBUG_TABLE") != nullptr;
     for (int mlog = 9; mlog <= 12; ++mlog) {
         const int M = 1 << mlog;
-        std::vector<double> nodes;
-        int J_side[2] = {0, 0};
-        bool ok = true;
-        for (int side = 0; side < 2 && ok; ++side) {  // 0: u = w (lower half), 1: u = 1 - w (upper half)
+        int J_side[2];
+        for (int side = 0; side < 2; ++side) {
             // number of levels: the last one (uniform down to w = 0) must resolve the end of the range
-            const long double z_end = side ? z_hi : z_lo;
+            const long double z_end = side ? s.z_hi : s.z_lo;
             int J = 0;
-            while (J < 40 && 0.5L * dg * ldexpl(1.0L, -(J + 1) - mlog) * abs_P1(z_end) / k2 > PS_RELBW_TABLE_ALPHA) ++J;
-            if (J >= 40) { ok = false; break; }
+            while (J < PS_RELBW_TABLE_MAX_J && 0.5L * s.dg * ldexpl(1.0L, -(J + 1) - mlog) * abs_P1(z_end) / s.k2 > PS_RELBW_TABLE_ALPHA) ++J;
             J_side[side] = J;
-            long double z = side ? 0.0L : 0.0L;  // Newton start; the first node of either half is u = 1/2
-            for (int j = 0; j <= J && ok; ++j) {
-                const bool last = j == J;
-                const long double edge = ldexpl(1.0L, last ? -(J + 1) : -(j + 1));          // w of node 0
-                const long double width = ldexpl(1.0L, last ? -(J + 1) : -(j + 2));
-                const long double half_h = 0.5L * dg * width / M;
-                for (int i = 0; i <= M; ++i) {
-                    const long double w = edge - width * i / M;
-                    const long double u = side ? 1.0L - w : w;
-                    z = relbw_root(g_lo + u * dg, kappa, z_lo, z_hi, z);
-                    if (half_h * abs_P1(z) / k2 > PS_RELBW_TABLE_ALPHA) { ok = false; break; }
-                    nodes.push_back((double)z);
+        }
+        for (int attempt = 0; attempt < 4; ++attempt) {
+            if (J_side[0] >= PS_RELBW_TABLE_MAX_J || J_side[1] >= PS_RELBW_TABLE_MAX_J) break;
+            const int n_levels = J_side[0] + J_side[1] + 2;
+            std::vector<double> nodes((size_t)n_levels * (M + 1));
+            std::vector<char> level_ok(n_levels, 0);
+            std::atomic<int> next{0};
+            auto worker = [&]() {
+                for (int l = next.fetch_add(1); l < n_levels; l = next.fetch_add(1)) {
+                    const int side = l > J_side[0] ? 1 : 0, j = side ? l - J_side[0] - 1 : l;
+                    level_ok[l] = relbw_table_level(s, side, j, J_side[side], mlog, nodes.data() + (size_t)l * (M + 1)) ? 1 : 0;
+                }
+            };
+            unsigned n_threads = std::thread::hardware_concurrency();
+            n_threads = n_threads < 1 ? 1 : (n_threads > 16 ? 16 : n_threads);
+            if ((int)n_threads > n_levels) n_threads = (unsigned)n_levels;
+            std::vector<std::thread> pool;
+            for (unsigned k = 1; k < n_threads; ++k) pool.emplace_back(worker);
+            worker();
+            for (std::thread& th : pool) th.join();
+            bool ok = true, grow = false;
+            for (int l = 0; l < n_levels; ++l) {
+                if (level_ok[l]) continue;
+                ok = false;
+                const int side = l > J_side[0] ? 1 : 0, j = side ? l - J_side[0] - 1 : l;
+                if (debug) fprintf(stderr, "relbw node table: 2^%d nodes per level, side %d, level %d of %d refused\n", mlog, side, j, J_side[side]);
+                if (j == J_side[side]) {  // the last level is too long: one more dyadic level
+                    ++J_side[side];
+                    grow = true;
+                } else {
+                    grow = false;  // a dyadic level needs more nodes: next mlog
+                    break;
                 }
             }
-        }
-        if (ok) {
-            t->tab_nodes.swap(nodes);
-            t->tab_mlog = mlog;
-            t->tab_J_lo = J_side[0];
-            t->tab_J_hi = J_side[1];
-            t->tab_kind = PS_MASS_RELBW;
-            return;
+            if (ok) {
+                t->tab_nodes.swap(nodes);
+                t->tab_mlog = mlog;
+                t->tab_J_lo = J_side[0];
+                t->tab_J_hi = J_side[1];
+                t->tab_kind = PS_MASS_RELBW;
+                return;
+            }
+            if (!grow) break;
         }
     }
 }

@@ -318,3 +318,76 @@ def test_node_tables_are_offered_per_sampler():
     assert size(chain(mf.breitwigner_factory)) == 0
     assert _lib.lib.ps_tree_relbw_nodes(chain(mf.gauss_factory).compile().handle) == 0
     assert size(ps.nbody_decay(5279.58, [139.57018] * 3)) == 0
+
+
+@pytest.mark.parametrize("case", [
+    (5279.58, 895.81, 47.4, 493.677, 139.57018, 0.0),                          # K*-like
+    (2010.26, 1864.84, 1.6050035525481589e-09, 493.677, 139.57039, 139.57039),  # a D0 with its physical width: kappa 5e12
+    (50000.0, 895.81, 47.4, 493.677, 139.57018, 0.0),                           # upper limit a thousand widths away
+    (5279.58, 775.26, 155.0, 139.57018, 139.57018, 139.57018),                  # broad: kappa 20
+], ids=["kstar", "d0_physical_width", "far_upper_limit", "kappa_20"])
+def test_relbw_node_table_matches_multiprecision_inverse_cdf(case):
+    """ps_tree_create's table for a relativistic Breit-Wigner with event-independent limits (ps_samplers.cuh
+    sample_relbw_table; mass_functions.py:70-102): the kernel's arithmetic, restated in numpy on the host copy of the
+    table, against a 50-digit inversion of the CDF, for draws all over [0, 1) and hard against both ends.  The nodes are
+    solved relative to the end of the mass range their half of the uniform approaches, so the reference is too.  Also
+    guards the cost of building it (this D0 once took 0.5 s, and was refused a table after 1.6 s below a D*+)."""
+    import time
+
+    import phasespace_b200 as ps
+    from phasespace_b200.fromdecay import mass_functions as mf
+
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    top, m, width, d1, d2, third = case
+    t0 = time.perf_counter()
+    tree = ps.GenParticle("X", top).set_children(
+        ps.GenParticle("R", mf.relativistic_breitwigner_factory(m, width)).set_children(
+            ps.GenParticle("a", d1), ps.GenParticle("b", d2)), ps.GenParticle("c", third))
+    tab, (kind, mlog, j_lo, j_hi), w_min = _node_table(tree)
+    assert time.perf_counter() - t0 < 0.4
+    assert kind == 3 and w_min == 0.0 and tab.size == ((j_lo + 1) + (j_hi + 1)) * ((1 << mlog) + 1)
+    # the constants as the host computes them in fp64 (ps_api.cu host_sampler_constants / host_sampler_limits)
+    a, b = m * m, m * width
+    p = np.sqrt(0.5 * (np.sqrt(a * a + b * b) + a))
+    q = b / (2.0 * p)
+    kappa = 2.0 * p / q
+    lo, hi = d1 + d2, top - third
+
+    def g_fp64(z):
+        return np.arctan(z) + np.arctan(z + kappa) + np.log(((z + kappa) ** 2 + 1.0) / (z * z + 1.0)) / kappa
+
+    d_g = g_fp64((hi - p) / q) - g_fp64((lo - p) / q)
+    rng = np.random.default_rng(3)
+    ends = np.ldexp(rng.random(40) + 0.5, -rng.integers(1, 52, 40))
+    u = np.concatenate([rng.random(120), ends, 1.0 - ends, [0.0, 0.5, 2.0 ** -51, 1 - 2.0 ** -51]])
+    u = np.floor(u * 2.0 ** 51) / 2.0 ** 51
+    idx, du, _ = _locate_node(u, mlog, j_lo, j_hi)
+    z = tab[idx]
+    h = du * d_g * (1.0 / (kappa * kappa + 4.0))
+    y = z + kappa
+    aa, bb = z * z + 1.0, y * y + 1.0
+    p1, p2, p3 = 2.0 * (z * bb + y * aa), 8.0 * z * y + 2.0 * (aa + bb), 12.0 * (y + z)
+    d = h * (aa * bb)
+    al, be, ga = h * p1, h * p2 * d, h * p3 * d * d
+    x = np.clip(p + q * (z + d * (1 + al / 2 + (be + al * al) / 6 + (ga + 4 * al * be + al ** 3) / 24)), lo, hi)
+
+    k_mp = mp.mpf(kappa)
+
+    def g_mp(t):
+        return mp.atan(t) + mp.atan(t + k_mp) + mp.log(((t + k_mp) ** 2 + 1) / (t * t + 1)) / k_mp
+
+    z_lo, z_hi = (mp.mpf(lo) - mp.mpf(p)) / mp.mpf(q), (mp.mpf(hi) - mp.mpf(p)) / mp.mpf(q)
+    g_lo, g_hi = g_mp(z_lo), g_mp(z_hi)
+    for uk, xk in zip(u, x):
+        if uk == 0.0:
+            assert xk == lo
+            continue
+        target = g_lo + mp.mpf(float(uk)) * mp.mpf(d_g) if uk < 0.5 else g_hi - (1 - mp.mpf(float(uk))) * mp.mpf(d_g)
+        z_true = mp.findroot(lambda t: g_mp(t) - target, mp.mpf(float((xk - p) / q)), tol=mp.mpf("1e-40"), maxsteps=200)
+        x_true = min(max(float(mp.mpf(p) + mp.mpf(q) * z_true), lo), hi)
+        zt = float(z_true)
+        # what one rounding of the CDF costs at this mass (tests/helpers/conditioning.py sampler_noise), plus the series'
+        # truncation at the table's design point (alpha <= 0.004: up to 2e-14 for a resonance as broad as the rho)
+        conditioning = 2.0 ** -53 * (zt * zt + 1.0) * ((zt + kappa) ** 2 + 1.0) / (kappa * kappa + 4.0) * q / x_true
+        assert abs(xk - x_true) / x_true <= 5e-14 + 8.0 * conditioning, (uk, xk, x_true)
