@@ -89,6 +89,12 @@ int32_t ps_tree_node_table_size(const ps_tree* tree);
  * distance from an end of the uniform's range below which the kernel leaves a draw to the library inverse. */
 int32_t ps_tree_node_table(const ps_tree* tree, double* out, int32_t capacity, int32_t* meta, double* w_min);
 int32_t ps_tree_is_aot(const ps_tree* tree, int32_t with_boost, int32_t with_debug_uniforms, uint32_t flags);
+/* Resolves the generator kernel of the tree ahead of its first ps_generate -- a registry lookup, or for a tree without an
+ * ahead-of-time kernel the NVRTC compilation (one to three seconds; cached in the process and on disk) -- on `device`
+ * (>= 0: made current in the calling thread first; < 0: the current device).  Thread-safe and concurrent: the modes of a
+ * GenMultiDecay (genmultidecay.py:155-197: one GenParticle.generate, i.e. one tf.function trace, per mode) are prepared
+ * by several host threads at once instead of one after the other inside the first generate(). */
+int ps_tree_prepare(const ps_tree* tree, int32_t with_boost, int32_t with_debug_uniforms, uint32_t flags, int32_t device);
 
 /* Replaces GenParticle.generate / _recursive_generate / _generate / _generate_part2
  * (phasespace.py:628-717, 497-626, 300-397, 399-495) and the rng.uniform calls of random.py:

@@ -52,6 +52,7 @@ def _load():
         "ps_tree_node_table_size": (i32, [vp]),
         "ps_tree_node_table": (i32, [vp, vp, i32, vp, vp]),
         "ps_tree_is_aot": (i32, [vp, i32, i32, u32]),
+        "ps_tree_prepare": (c.c_int, [vp, i32, i32, u32, i32]),
         "ps_generate": (c.c_int, [vp, u64, u64, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, u32, vp, dbl]),
         "ps_generate_indexed": (c.c_int, [vp, u64, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, u32, vp]),
         "ps_generate_host": (c.c_int, [vp, u64, u64, i64, vp, i64, vp, vp, vp, i64, u32]),

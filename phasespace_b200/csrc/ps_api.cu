@@ -746,35 +746,33 @@ struct Nvrtc {
 
 Nvrtc* load_nvrtc() {
     static Nvrtc n;
-    static bool tried = false;
-    if (tried) return n.handle ? &n : nullptr;
-    tried = true;
-    // The toolkit's own NVRTC first (CUDA 12.9 emits PTX ISA 8.8, needed for 256-bit stores); a process
-    // that already holds an older libnvrtc.so.12 (e.g. the one bundled with torch) is found last.
-    const char* names[] = {getenv("PS_NVRTC_PATH"), "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so",
-                           "libnvrtc.so.12", "libnvrtc.so"};
-    for (const char* nm : names) {
-        if (!nm || !*nm) continue;
-        n.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
-        if (n.handle) break;
-    }
-    if (!n.handle) return nullptr;
-#define PS_SYM(field, sym) *(void**)(&n.field) = dlsym(n.handle, sym)
-    PS_SYM(CreateProgram, "nvrtcCreateProgram");
-    PS_SYM(CompileProgram, "nvrtcCompileProgram");
-    PS_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
-    PS_SYM(GetProgramLog, "nvrtcGetProgramLog");
-    PS_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
-    PS_SYM(GetCUBIN, "nvrtcGetCUBIN");
-    PS_SYM(DestroyProgram, "nvrtcDestroyProgram");
-    PS_SYM(GetErrorString, "nvrtcGetErrorString");
-    PS_SYM(Version, "nvrtcVersion");
+    static std::once_flag once;  // several threads may ask for their first NVRTC compilation at once (ps_tree_prepare)
+    std::call_once(once, [] {
+        // The toolkit's own NVRTC first (CUDA 12.9 emits PTX ISA 8.8, needed for 256-bit stores); a process
+        // that already holds an older libnvrtc.so.12 (e.g. the one bundled with torch) is found last.
+        const char* names[] = {getenv("PS_NVRTC_PATH"), "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so",
+                               "libnvrtc.so.12", "libnvrtc.so"};
+        void* handle = nullptr;
+        for (const char* nm : names) {
+            if (!nm || !*nm) continue;
+            handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (handle) break;
+        }
+        if (!handle) return;
+#define PS_SYM(field, sym) *(void**)(&n.field) = dlsym(handle, sym)
+        PS_SYM(CreateProgram, "nvrtcCreateProgram");
+        PS_SYM(CompileProgram, "nvrtcCompileProgram");
+        PS_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+        PS_SYM(GetProgramLog, "nvrtcGetProgramLog");
+        PS_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+        PS_SYM(GetCUBIN, "nvrtcGetCUBIN");
+        PS_SYM(DestroyProgram, "nvrtcDestroyProgram");
+        PS_SYM(GetErrorString, "nvrtcGetErrorString");
+        PS_SYM(Version, "nvrtcVersion");
 #undef PS_SYM
-    if (!n.CreateProgram || !n.CompileProgram || !n.GetCUBIN) {
-        n.handle = nullptr;
-        return nullptr;
-    }
-    return &n;
+        if (n.CreateProgram && n.CompileProgram && n.GetCUBIN) n.handle = handle;
+    });
+    return n.handle ? &n : nullptr;
 }
 
 // On-disk cache of NVRTC results: $PS_B200_CACHE_DIR, else $XDG_CACHE_HOME/phasespace_b200, else
@@ -822,7 +820,8 @@ bool read_file(const std::string& path, std::vector<char>& out) {
 }
 
 void write_file_atomic(const std::string& path, const std::vector<char>& data) {
-    const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+    static std::atomic<unsigned> serial{0};  // two threads may write (different or, rarely, the same) files at once
+    const std::string tmp = path + ".tmp" + std::to_string((long long)getpid()) + "_" + std::to_string(serial.fetch_add(1));
     FILE* f = fopen(tmp.c_str(), "wb");
     if (!f) return;
     const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
@@ -930,14 +929,22 @@ int get_kernel(const ps_tree* t, int variant, int boost, int dbg, int exact, con
 int get_kernel_slow(const ps_tree* t, int variant, int boost, int dbg, int exact, const void** fn) {
     KernelKey key{t->signature, variant, boost, dbg, exact};
     Registry& r = registry();
+    {
+        std::lock_guard<std::mutex> lock(r.mu);
+        auto it = r.aot.find(key);
+        if (it != r.aot.end()) { *fn = it->second; return 0; }
+        it = r.jit.find(key);
+        if (it != r.jit.end()) { *fn = it->second; return 0; }
+    }
+    // NVRTC takes one to three seconds per tree: compiled OUTSIDE the registry lock, so that the modes of a GenMultiDecay
+    // can be prepared by several host threads at once (ps_tree_prepare).  Two threads asking for the same new tree at the
+    // same moment both compile it; the first result is kept.
+    const void* compiled = nullptr;
+    int rc = jit_compile(key, &compiled);
+    if (rc) return rc;
     std::lock_guard<std::mutex> lock(r.mu);
-    auto it = r.aot.find(key);
-    if (it != r.aot.end()) { *fn = it->second; return 0; }
-    it = r.jit.find(key);
-    if (it != r.jit.end()) { *fn = it->second; return 0; }
-    int rc = jit_compile(key, fn);
-    if (rc == 0) r.jit[key] = *fn;
-    return rc;
+    *fn = r.jit.emplace(key, compiled).first->second;
+    return 0;
 }
 
 // Launch shape (see genbod_body): a persistent grid of SM count x resident CTAs with a static tile stride;
@@ -1107,6 +1114,14 @@ extern "C" int ps_generate_indexed(const ps_tree* tree, uint64_t seed, const int
                          weights_max, particles, particle_stride, stats, err_flag, flags);
     if (rc) return rc;
     return launch_generate(tree, p, flags, stream);
+}
+
+extern "C" int ps_tree_prepare(const ps_tree* tree, int32_t with_boost, int32_t with_debug_uniforms, uint32_t flags,
+                               int32_t device) {
+    if (!tree) return fail(PS_E_INVALID, "null tree");
+    if (device >= 0) PS_CUDA(cudaSetDevice(device));
+    const void* fn = nullptr;
+    return get_kernel(tree, PS_VARIANT_GENERATE, with_boost ? 1 : 0, with_debug_uniforms ? 1 : 0, (flags & PS_GEN_EXACT) ? 1 : 0, &fn);
 }
 
 // ---------------------------------------------------------------------------------- host-buffer path

@@ -8,7 +8,7 @@ from collections.abc import Callable
 import numpy as np
 import torch
 
-from ..phasespace import GenParticle
+from ..phasespace import GenParticle, prepare_all
 from ..random import Generator, get_rng
 from . import pdg
 from .mass_functions import DEFAULT_CONVERTER
@@ -84,6 +84,9 @@ class GenMultiDecay:
         # collected and checked with a single synchronisation at the end
         main = torch.cuda.current_stream()
         populated = [(gen, int(n)) for (_, gen), n in zip(self.gen_particles, counts) if n > 0]
+        # kernels of modes seen for the first time are compiled side by side, not one inside each generate() below
+        prepare_all([gen.compile() for gen, _ in populated], boost=kwargs.get("boost_to") is not None,
+                    exact=bool(kwargs.get("exact")))
         n_streams = min(len(populated), self.MAX_STREAMS)
         streams = self._stream_pool(n_streams) if n_streams > 1 else []
         for st in streams:

@@ -156,6 +156,7 @@ class CompiledDecay:
         self.structure = _structure(top)
         self.epoch = _TREE_EPOCH
         self._err_flags = {}
+        self._prepared = set()
         self._static_forbidden = self._check_static()
         # the plain call of generate(): no per-event failure mode, no Python mass functions, nothing forbidden
         self.plain_ok = (not self.has_resonances and not self.top_is_resonance and self.n_user == 0
@@ -181,6 +182,16 @@ class CompiledDecay:
                 if not (float(part._mass_val) - total >= 0.0):
                     return part.name
         return None
+
+    def prepare(self, boost: bool = False, debug: bool = False, exact: bool = False, device_index: int = -1):
+        """Resolve the generator kernel ahead of the first launch (``ps_tree_prepare``): for a tree without an
+        ahead-of-time kernel that is the NVRTC compilation.  ctypes releases the GIL for the call, so several trees can
+        be prepared from several threads at once (``prepare_all``)."""
+        key = (bool(boost), bool(debug), bool(exact), int(device_index))
+        if key not in self._prepared:
+            flags = _lib.PS_GEN_EXACT if exact else 0
+            _lib.check(_lib.lib.ps_tree_prepare(self.handle, int(boost), int(debug), flags, int(device_index)))
+            self._prepared.add(key)
 
     # ------------------------------------------------------------------ resonances sampled by Python callables
     def presample(self, n_events: int, top_mass, device):
@@ -303,6 +314,26 @@ class CompiledDecay:
         )
         _lib.check(rc)
         return weights, weights_max, particles, err
+
+
+def prepare_all(compiled, boost=False, exact=False, device_index=None, max_workers=None):
+    """Prepare the kernels of several compiled trees concurrently (one NVRTC compilation per tree that has no
+    ahead-of-time kernel, one to three seconds each): the reference retraces one ``tf.function`` per decay mode one after
+    the other; here the modes of a ``GenMultiDecay`` compile side by side on the host's cores."""
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    todo = [c for c in compiled if (bool(boost), False, bool(exact), int(device_index)) not in c._prepared]
+    if not todo:
+        return
+    if len(todo) == 1:
+        todo[0].prepare(boost, False, exact, device_index)
+        return
+    import concurrent.futures
+    import os
+
+    workers = max_workers or min(len(todo), os.cpu_count() or 4, 16)
+    with concurrent.futures.ThreadPoolExecutor(workers) as pool:
+        list(pool.map(lambda c: c.prepare(boost, False, exact, device_index), todo))
 
 
 class GenParticle:

@@ -112,3 +112,53 @@ def test_weight_scale_is_refused_where_it_cannot_be_folded():
         comp.launch(1000, seed=1, weight_scale=0.5, boost_to=torch.tensor([[0.0, 0.0, 100.0, 6000.0]], dtype=torch.float64, device="cuda"))
     with pytest.raises(ValueError, match="weight_scale"):
         comp.launch(1000, seed=1, weight_scale=float("nan"))
+
+
+def test_modes_are_compiled_side_by_side(tmp_path, monkeypatch):
+    """Kernels of decay modes that have no ahead-of-time kernel are compiled by NVRTC (1-3 s each).  GenMultiDecay
+    prepares all populated modes concurrently before the first launch (ps_tree_prepare; the reference traces one
+    tf.function per mode, one after the other, genmultidecay.py:185-190): with an empty on-disk cache the first
+    generate() of six new trees must cost well under six single compilations, every mode ends up prepared, and the
+    events do not depend on who compiled the kernel."""
+    import time
+
+    from phasespace_b200.phasespace import prepare_all
+
+    monkeypatch.setenv("PS_B200_CACHE_DIR", str(tmp_path))
+
+    def modes(tag):
+        out = []
+        for k in range(6):  # six tree shapes no other test uses: 3 + k bodies below a two-body decay
+            sub = phasespace.GenParticle(f"X{tag}", 3000.0 + k).set_children(
+                *[phasespace.GenParticle(f"x{tag}{j}", 100.0 + j) for j in range(3 + k)])
+            top = phasespace.GenParticle(f"T{tag}", 9000.0).set_children(
+                sub, phasespace.GenParticle(f"g{tag}", 0.0), phasespace.GenParticle(f"h{tag}", 500.0 + k))
+            out.append((1.0 / 6.0, top))
+        return out
+
+    gmd = GenMultiDecay(modes("a"))
+    t0 = time.perf_counter()
+    w_a, ev_a = gmd.generate(6000, seed=5)
+    torch.cuda.synchronize()
+    first = time.perf_counter() - t0
+    # one more tree of the size of the largest mode (another shape: the six above are in the process by now), alone
+    single = phasespace.GenParticle("Ts", 9000.0).set_children(
+        phasespace.GenParticle("Xs", 3000.0).set_children(*[phasespace.GenParticle(f"xs{j}", 100.0 + j) for j in range(8)]),
+        phasespace.GenParticle("gs", 0.0), phasespace.GenParticle("hs", 500.0), phasespace.GenParticle("is", 139.57)).compile()
+    t0 = time.perf_counter()
+    single.prepare(device_index=torch.cuda.current_device())
+    one = time.perf_counter() - t0
+    assert all(gen.compile()._prepared for _, gen in gmd.gen_particles)
+    import os
+
+    if (os.cpu_count() or 1) >= 4:
+        assert first < 4.0 * one + 2.0, (first, one)  # six trees, the largest of which alone took `one`
+    # the same modes again, now from the registry of the process and prepared one by one
+    gmd_b = GenMultiDecay(modes("b"))
+    for _, gen in gmd_b.gen_particles:
+        prepare_all([gen.compile()])
+    w_b, ev_b = gmd_b.generate(6000, seed=5)
+    assert len(w_a) == len(w_b) == 6
+    for wa, wb, ea, eb in zip(w_a, w_b, ev_a, ev_b):
+        assert torch.equal(wa, wb)
+        assert all(torch.equal(ea[ka], eb[kb]) for ka, kb in zip(ea, eb))
