@@ -60,6 +60,30 @@ class GenMultiDecay:
         )
         return cls(gen_particles)
 
+    def mode_counts(self, n_events: int, rng: Generator):
+        """Events per decay mode: one multinomial draw with the mode probabilities (genmultidecay.py:165-183), from the
+        generator's seed and one reserved counter -- a pure function of (seed, offset), so every rank of a sharded job
+        computes the same split on its host."""
+        probs = np.asarray([float(dm[0]) for dm in self.gen_particles], dtype=np.float64)
+        probs = probs / probs.sum()
+        split_rng = np.random.Generator(np.random.Philox(key=rng.seed ^ 0x5DEECE66D, counter=rng.reserve(1)))
+        return split_rng.multinomial(int(n_events), probs)
+
+    def generate_sharded(self, n_events: int, normalize_weights: bool = True, *, rank: int | None = None,
+                         world: int | None = None, group=None, **kwargs):
+        """This rank's share of ``generate(n_events, ...)``: the mode counts come from the seed and
+        are the same on every rank, and rank r generates the contiguous slice ``shard_range(n_mode, r, world)`` of every
+        populated mode's events, with the event indices the single-GPU call would have used.  The concatenation over
+        ranks of each mode's tensors is therefore bit-identical to the single-GPU result.  No collective on the data
+        path; the only exchange is one MAX all-reduce of a scalar when the global maximum weight is not known beforehand
+        (modes with ``boost_to`` or resonant leaves).  ``rank`` / ``world`` default to the process group's.  Returns what
+        ``generate`` returns, each list entry holding this rank's events of that mode (possibly zero of them)."""
+        from ..sharding import _rank_world
+
+        if rank is None or world is None:
+            rank, world = _rank_world(group)
+        return self.generate(n_events, normalize_weights, _shard=(int(rank), int(world), group), **kwargs)
+
     def generate(self, n_events: int, normalize_weights: bool = True, **kwargs):
         """Generate four-momenta from the decay modes (genmultidecay.py:155-197).
 
@@ -75,10 +99,8 @@ class GenMultiDecay:
         """
         n_events = int(n_events)
         rng = get_rng(kwargs.pop("seed", None))
-        probs = np.asarray([float(dm[0]) for dm in self.gen_particles], dtype=np.float64)
-        probs = probs / probs.sum()
-        split_rng = np.random.Generator(np.random.Philox(key=rng.seed ^ 0x5DEECE66D, counter=rng.reserve(1)))
-        counts = split_rng.multinomial(n_events, probs)
+        shard = kwargs.pop("_shard", None)
+        counts = self.mode_counts(n_events, rng)
         weights, max_weights, events = [], [], []
         # one kernel per populated mode, fanned out over a few CUDA streams; forbidden-decay flags are
         # collected and checked with a single synchronisation at the end
@@ -102,18 +124,30 @@ class GenMultiDecay:
             if not all(np.isfinite(w) and w > 0 for w in mode_w_max):
                 mode_w_max = None
         total_w_max = max(mode_w_max) if mode_w_max else None
+        if shard is not None:
+            from ..sharding import shard_range
+
+            boost = kwargs.get("boost_to")
+            if boost is not None and np.shape(boost)[0] != 1 and len(populated) > 0:
+                raise ValueError("sharded GenMultiDecay takes one boost_to row for all events, not one per event")
+            if any(gen.compile().n_user for gen, _ in populated):
+                raise ValueError("sharded generation needs in-kernel mass functions (no arbitrary Python callables)")
         for k, (gen, n) in enumerate(populated):
             if mode_w_max:
                 call = dict(normalize_weights=True, _weight_scale=mode_w_max[k] / total_w_max)
             else:
                 call = dict(normalize_weights=False)
+            mode_rng, n_here = rng, n
+            if shard is not None:  # this rank's slice of the mode's events, at the indices the unsharded call uses
+                lo, n_here = shard_range(n, shard[0], shard[1])
+                mode_rng = Generator(rng.seed, rng.reserve(n) + lo)
             if streams:
                 with torch.cuda.stream(streams[k % n_streams]):
-                    out = gen.generate(n, seed=rng, _deferred_checks=checks, **call, **kwargs)
+                    out = gen.generate(n_here, seed=mode_rng, _deferred_checks=checks, **call, **kwargs)
                 for t in (out[0], next(iter(out[-1].values()))):
                     t.record_stream(main)  # the slab was allocated on the side stream and is consumed on `main`
             else:
-                out = gen.generate(n, seed=rng, _deferred_checks=checks, **call, **kwargs)
+                out = gen.generate(n_here, seed=mode_rng, _deferred_checks=checks, **call, **kwargs)
             weights.append(out[0])
             max_weights.append(None if mode_w_max else out[1])
             events.append(out[-1])
@@ -126,7 +160,12 @@ class GenMultiDecay:
         if normalize_weights:
             if mode_w_max:
                 return weights, events
-            total_max = torch.stack([mw.max() for mw in max_weights]).max()  # genmultidecay.py:193
+            local = [mw.max() for mw in max_weights if mw.numel()]  # genmultidecay.py:193
+            total_max = torch.stack(local).max() if local else torch.zeros((), dtype=torch.float64, device=weights[0].device if weights else "cuda")
+            if shard is not None and shard[1] > 1:
+                from ..sharding import allreduce_max
+
+                total_max = allreduce_max(total_max, shard[2], world=shard[1])
             return [w / total_max for w in weights], events
         return weights, max_weights, events
 

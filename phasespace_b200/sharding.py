@@ -90,6 +90,20 @@ def allreduce_count(count: int, device=None, group=None) -> int:
     return int(t.item())
 
 
+def allreduce_max(t: torch.Tensor, group=None, world: int | None = None) -> torch.Tensor:
+    """MAX over ranks of a small tensor (the global maximum weight of a sharded ``GenMultiDecay``, genmultidecay.py:193).
+    ``world`` > 1 without an initialised process group is an error: the ranks could not agree on the maximum."""
+    if not (dist.is_available() and dist.is_initialized()):
+        if world is not None and world > 1:
+            raise RuntimeError("a global maximum over ranks needs an initialised torch.distributed process group")
+        return t
+    if dist.get_world_size(group) == 1:
+        return t
+    out = t.clone()
+    dist.all_reduce(out, op=dist.ReduceOp.MAX, group=group)
+    return out
+
+
 def allreduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
     """SUM all-reduce of a small tensor (histograms, counters); identity in a single process."""
     out = t.clone()

@@ -163,3 +163,40 @@ def test_modes_are_compiled_side_by_side(tmp_path, monkeypatch):
     for wa, wb, ea, eb in zip(w_a, w_b, ev_a, ev_b):
         assert torch.equal(wa, wb)
         assert all(torch.equal(ea[ka], eb[kb]) for ka, kb in zip(ea, eb))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_multidecay_is_bit_identical(world):
+    """the mode counts come from the seed, every rank generates a contiguous slice of every mode at the
+    event indices the single-GPU call uses -- the concatenation over ranks equals the single-GPU result bit for bit, with
+    no collective (the global maximum weight of these chains is known on the host)."""
+    container = GenMultiDecay.from_dict(example_decay_chains.dstarplus_big_decay, tolerance=1e-10)
+    n = 50_001
+    w_ref, ev_ref = container.generate(n, seed=11)
+    shares = [container.generate_sharded(n, seed=11, rank=r, world=world) for r in range(world)]
+    assert all(len(s[0]) == len(w_ref) for s in shares)
+    for k, (w, ev) in enumerate(zip(w_ref, ev_ref)):
+        assert torch.equal(torch.cat([s[0][k] for s in shares]), w)
+        for name, vec in ev.items():
+            assert torch.equal(torch.cat([s[1][k][name] for s in shares]), vec)
+    # unnormalised weights come with their maximum weights, sharded the same way
+    w3, mw3, _ = container.generate(n, normalize_weights=False, seed=12)
+    parts = [container.generate_sharded(n, normalize_weights=False, seed=12, rank=r, world=world) for r in range(world)]
+    for k in range(len(w3)):
+        assert torch.equal(torch.cat([p[0][k] for p in parts]), w3[k])
+        assert torch.equal(torch.cat([p[1][k] for p in parts]), mw3[k])
+
+
+def test_sharded_multidecay_needs_a_process_group_for_a_global_maximum():
+    """Modes whose maximum weight depends on the event (boost_to) are normalised by the maximum over ALL ranks: one scalar
+    MAX all-reduce (tests/test_sharding_gloo.py runs it on two ranks).  One rank is the identity; several ranks without a
+    process group are refused instead of normalising each share by its own maximum."""
+    container = GenMultiDecay.from_dict(example_decay_chains.dplus_4grandbranches, tolerance=1e-10)
+    boost = torch.tensor([[0.0, 0.0, 3000.0, (3000.0 ** 2 + 1869.66 ** 2) ** 0.5]], dtype=torch.float64)
+    w_ref, _ = container.generate(2000, seed=3, boost_to=boost)
+    w_one, _ = container.generate_sharded(2000, seed=3, boost_to=boost, rank=0, world=1)
+    assert all(torch.equal(a, b) for a, b in zip(w_ref, w_one))
+    with pytest.raises(RuntimeError):
+        container.generate_sharded(2000, seed=3, boost_to=boost, rank=0, world=2)
+    with pytest.raises(ValueError):
+        container.generate_sharded(2000, seed=3, boost_to=boost.expand(2000, 4), rank=0, world=2)
