@@ -284,16 +284,20 @@ __device__ __forceinline__ double sample_relbw_table(const SamplerConst& k, cons
 // Draws closer to an end of the range than w_min (only where an end lies so far out that Phi there is 0 or 1 in fp64, and
 // then only u = 0 from the generator's own 51-bit stream) are left to the library path by the caller.
 // ~40 instructions (21 fp64) instead of ~180 (normcdfinv).
+// (coefficients in __constant__ memory: read as constant-bank operands of the DFMA instead of being materialised with
+// two moves each, as in ps_fastmath.cuh)
+static __constant__ double kGaussSeries[9] = {1.0 / 3.0, 1.0 / 6.0, 7.0 / 24.0, 0.2, 23.0 / 60.0, 7.0 / 120.0,
+                                              1.0 / 6.0, 163.0 / 360.0, 127.0 / 720.0};
 __device__ __forceinline__ double sample_gauss_table(const SamplerConst& k, const double* lim, const double* tab, int idx,
                                                      double du, double lo, double hi) {
     const double2 node = __ldg(reinterpret_cast<const double2*>(tab) + idx);
     const double z = node.x;
     const double d = du * lim[1] * node.y;     // (u - u_node) (Phi(b) - Phi(a)) / phi(z)
     const double z2 = z * z;
-    const double c3 = fma(z2, 1.0 / 3.0, 1.0 / 6.0);
-    const double c4 = z * fma(z2, 0.25, 7.0 / 24.0);
-    const double c5 = fma(z2, fma(z2, 0.2, 23.0 / 60.0), 7.0 / 120.0);
-    const double c6 = z * fma(z2, fma(z2, 1.0 / 6.0, 163.0 / 360.0), 127.0 / 720.0);
+    const double c3 = fma(z2, kGaussSeries[0], kGaussSeries[1]);
+    const double c4 = z * fma(z2, 0.25, kGaussSeries[2]);
+    const double c5 = fma(z2, fma(z2, kGaussSeries[3], kGaussSeries[4]), kGaussSeries[5]);
+    const double c6 = z * fma(z2, fma(z2, kGaussSeries[6], kGaussSeries[7]), kGaussSeries[8]);
     const double corr = fma(d, fma(d, fma(d, fma(d, fma(d, c6, c5), c4), c3), 0.5 * z), 1.0);
     return clamp_mass(fma(k.w, fma(d, corr, z), k.m), lo, hi);
 }
