@@ -950,6 +950,9 @@ int get_kernel_slow(const ps_tree* t, int variant, int boost, int dbg, int exact
 // Launch shape (see genbod_body): a persistent grid of SM count x resident CTAs with a static tile stride;
 // for trees with at most PS_CHUNKED_MAX_P particles (memory-bound) a covering grid with up to 16
 // consecutive tiles per CTA.
+#ifndef PS_PDL_MAX_EVENTS
+#define PS_PDL_MAX_EVENTS (1LL << 21) /* launches of at most this many events opt into programmatic dependent launch */
+#endif
 // Dynamic shared memory (unused by the kernel) that makes a second CTA of the same kernel not fit on an SM.
 #define PS_ONE_CTA_SMEM (116 * 1024)
 
@@ -1078,7 +1081,31 @@ int launch_generate(const ps_tree* t, PsParams& p, uint32_t flags, void* stream)
     rc = pick_grid(t, fn, boost, dbg, exact, p.n_events, &grid, &p.tiles_per_cta, &dyn_smem);
     if (rc) return rc;
     void* args[] = {&p};
-    PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, dyn_smem, (cudaStream_t)stream));
+    // Programmatic stream serialisation (ps_kernel.cuh pdl_prologue): this launch's CTAs may become resident while the
+    // previous grid's last wave drains.  Only for small calls: measured on a B200 (profiles/r02_ab_pdl.log), 1e6 two-body
+    // events 13.7 -> 11.4 us per call (5.2 -> 6.3 TB/s), K* gamma 22.8 -> 21.3, 3e5 events 10.2 -> 8.7; but a memory-bound
+    // grid of many waves whose first wave was placed as slots happened to free up streams 2-6 % slower than one dispatched
+    // onto an empty chip (K* gamma, 3e6 and 1e7 events), and at 1e8 events there is nothing to gain.
+    // PS_B200_NO_PDL=1 launches everything plainly (A/B measurements).
+    static const bool pdl = [] {
+        const char* e = getenv("PS_B200_NO_PDL");
+        return !(e && *e && *e != '0');
+    }();
+    if (pdl && p.n_events <= PS_PDL_MAX_EVENTS) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(PS_BLOCK);
+        cfg.dynamicSmemBytes = dyn_smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PS_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    } else {
+        PS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PS_BLOCK), args, dyn_smem, (cudaStream_t)stream));
+    }
     g_launches.fetch_add(1);
     return 0;
 }

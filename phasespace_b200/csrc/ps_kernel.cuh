@@ -1038,6 +1038,9 @@ __host__ __device__ constexpr bool use_turn_table() {
 #ifndef PS_SPECIALIZE
 #define PS_SPECIALIZE 1
 #endif
+#ifndef PS_PDL
+#define PS_PDL 1
+#endif
 template <class Tree, bool BOOST, bool DBG, bool PLAIN, bool STATS>
 __device__ __forceinline__ void genbod_body_impl(const PsParams& prm) {
     constexpr int P = Tree::n_below;
@@ -1171,8 +1174,23 @@ __device__ __forceinline__ void genbod_body_impl(const PsParams& prm) {
     }
 }
 
+// Programmatic dependent launch (launch_generate in ps_api.cu sets the stream-serialisation attribute): as soon as every
+// CTA of this grid has started, the CTAs of the NEXT launch in the stream may take the SM slots that this grid's last wave
+// frees, and sit behind their own `wait` until this grid has completed and its stores are visible.  Nothing is read or
+// written before the wait, so the ordering every caller relies on (inputs produced by, and output memory recycled from,
+// earlier work in the stream) is unchanged; what is saved is the launch latency and the ramp of back-to-back calls --
+// the 1e6-event calls of the reference's benchmark protocol, the per-mode launches of a GenMultiDecay, the chunks of
+// generate_host and of the unweighting.  Both instructions are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_prologue() {
+#if PS_PDL
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 template <class Tree, bool BOOST, bool DBG>
 __device__ __forceinline__ void genbod_body(const PsParams& prm) {
+    pdl_prologue();
 #if PS_SPECIALIZE
     if constexpr (!DBG) {  // the debug kernels are for parity, not for speed: one body
         if (!prm.event_index && prm.normalize) {
