@@ -629,3 +629,42 @@ def test_children_added_to_a_leaf_after_compilation():
     assert float((parts["K+"] + parts["pi-"] - parts["K*0"]).abs().max()) / B0_MASS < 1e-12
     with pytest.raises(RuntimeError):
         kstar.set_children(GenParticle("x", 1.0), GenParticle("y", 1.0))
+
+
+def test_back_to_back_small_calls_keep_stream_order():
+    """Small launches opt into programmatic dependent launch (ps_kernel.cuh pdl_prologue): the next call's CTAs may
+    become resident while the previous grid drains, but nothing is read or written before `griddepcontrol.wait`.  What a
+    caller relies on must hold: (a) calls that write the SAME buffers one after the other leave the last call's events
+    there (output memory recycled by the allocator is exactly this case); (b) a boost_to array rewritten on the stream
+    between the calls is read as it stands at each call; (c) a consumer kernel that follows sees complete results."""
+    n, dev = 200_000, torch.device("cuda")
+    comp = phasespace.nbody_decay(B0_MASS, [PION_MASS, D.KAON_MASS]).compile()
+    out = {"weights": torch.empty((n,), dtype=torch.float64, device=dev),
+           "particles": torch.empty((2, n, 4), dtype=torch.float64, device=dev)}
+    err = torch.zeros((1,), dtype=torch.int32, device=dev)
+    sums = []
+    for seed in range(1, 41):
+        comp.launch(n, seed, out=out, err=err)
+        sums.append(out["particles"][:, :, 0].sum())  # a torch kernel right behind ours
+    torch.cuda.synchronize()
+    w_last, _, p_last, _ = comp.launch(n, 40)
+    assert torch.equal(out["weights"], w_last) and torch.equal(out["particles"], p_last)
+    for seed in (1, 17, 39):
+        _, _, p, _ = comp.launch(n, seed)
+        assert float(sums[seed - 1]) == float(p[:, :, 0].sum())
+    # (b) the input changes on the stream between the calls
+    four = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 4).compile()
+    boost = torch.tensor([[0.0, 0.0, 1000.0, (1000.0 ** 2 + B0_MASS ** 2) ** 0.5]], dtype=torch.float64, device=dev).repeat(n, 1)
+    got = []
+    for k in range(12):
+        boost[:, 2] += 500.0
+        boost[:, 3] = torch.sqrt(boost[:, 2] ** 2 + B0_MASS ** 2)
+        w, _, p, _ = four.launch(n, 7, boost_to=boost)
+        got.append((w, p))
+    torch.cuda.synchronize()
+    for k in (0, 5, 11):
+        pz = 1000.0 + 500.0 * (k + 1)
+        ref_boost = torch.tensor([[0.0, 0.0, pz, (pz ** 2 + B0_MASS ** 2) ** 0.5]], dtype=torch.float64, device=dev).repeat(n, 1)
+        w, _, p, _ = four.launch(n, 7, boost_to=ref_boost)
+        torch.cuda.synchronize()
+        assert torch.equal(got[k][0], w) and torch.equal(got[k][1], p)
