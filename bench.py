@@ -394,7 +394,9 @@ def run_b200(args, rank, local_rank, world):
                              "normalize_weights=True", "events_per_gpu_per_launch": n1, "kernel_ms": ms,
                  "events_per_s": ev_s, **bounds(ev_s / world, 72, "flat_2body"), "clocks": clk,
                  "l2": "72 MB of outputs per launch fit in the 126 MB L2: launches rotate over four output slabs (288 MB)",
-                 "note": "a 1e6-event launch lasts ~20 us: launch latency and the grid's ramp, not bandwidth, bound it"}
+                 "note": "a 1e6-event launch writes 72 MB (10 us at full bandwidth); the rest is the gap between two kernels "
+                         "of a stream and the ramp of the grid, which programmatic dependent launch (launches of at most "
+                         "2^21 events) partly hides; the Python launch loop itself costs ~9 us per call"}
         # the reference benchmark's protocol (benchmark/bench_phasespace.py:109-133): generate(1e6) per call through the
         # public API (allocation of the outputs included), 1 warm-up + 10 timed calls
         def do_run(k):  # benchmark/bench_phasespace.py:131-133: the result is returned and dropped
