@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PS_ABI_VERSION 3
+#define PS_ABI_VERSION 4
 
 /* mass model of a particle (GenParticle(name, mass): phasespace.py:100-119) */
 #define PS_MASS_FIXED 0 /* float mass: has_fixed_mass (phasespace.py:186-189) */

@@ -16,7 +16,7 @@ PS_MASS_FIXED, PS_MASS_GAUSS, PS_MASS_BW, PS_MASS_RELBW, PS_MASS_USER = range(5)
 PS_GEN_NORMALIZE, PS_GEN_EXACT = 1, 2
 PS_E_INVALID, PS_E_CUDA, PS_E_COMPILE, PS_E_FORBIDDEN = -1, -2, -3, -4
 TILE = 256  # events per tile of the unweighting mask kernel
-ABI_VERSION = 3  # PS_ABI_VERSION of include/phasespace_b200.h this binding was written against
+ABI_VERSION = 4  # PS_ABI_VERSION of include/phasespace_b200.h this binding was written against
 
 
 class NodeDesc(ctypes.Structure):

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported():
     for name in names:
         assert hasattr(raw, name), name
     assert set(names) == set(_lib.EXPORTS)
-    assert _lib.lib.ps_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.lib.ps_abi_version() == _lib.ABI_VERSION == 4
 
 
 def _tree(desc):
