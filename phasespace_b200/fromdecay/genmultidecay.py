@@ -18,6 +18,7 @@ class GenMultiDecay:
     MASS_WIDTH_TOLERANCE = 0.01
     DEFAULT_MASS_FUNC = "relbw"
     MAX_STREAMS = 8  # CUDA streams the per-mode kernels are spread over
+    MIN_EVENTS_FOR_STREAMS = 1 << 23  # calls with fewer events stay on the current stream
 
     def __init__(self, gen_particles: list[tuple[float, GenParticle]]):
         """A ``GenParticle``-type container that can handle multiple decays (genmultidecay.py:18-26).
@@ -109,11 +110,22 @@ class GenMultiDecay:
         # kernels of modes seen for the first time are compiled side by side, not one inside each generate() below
         prepare_all([gen.compile() for gen, _ in populated], boost=kwargs.get("boost_to") is not None,
                     exact=bool(kwargs.get("exact")))
-        n_streams = min(len(populated), self.MAX_STREAMS)
+        # Side streams pay when the modes' kernels are long enough to overlap their tails; a call of a few million events
+        # over a dozen modes is a row of small launches, cheapest issued back to back on the current stream (where each
+        # also overlaps the drain of the one before: programmatic dependent launch).
+        n_streams = min(len(populated), self.MAX_STREAMS) if n_events >= self.MIN_EVENTS_FOR_STREAMS else 1
         streams = self._stream_pool(n_streams) if n_streams > 1 else []
+        # nothing but n_events, normalize_weights and the seed: every mode that can goes through generate_fast, and all of
+        # them share one sticky forbidden-decay flag (zeroed on `main` BEFORE the side streams start waiting on it)
+        fast = not kwargs and len(populated) > 0
+        device = torch.device("cuda", torch.cuda.current_device())
+        checks = []
+        shared_err = None
+        if fast:
+            shared_err = torch.zeros((1,), dtype=torch.int32, device=device)
+            checks.append(shared_err)
         for st in streams:
             st.wait_stream(main)
-        checks = []
         # genmultidecay.py:192-195 divides every mode's weights by the largest maximum weight of all modes.  When every
         # populated mode has an event-independent maximum weight (particles at rest with fixed-mass leaves: what a
         # DecayLanguage chain gives) that number is known before anything is generated, and each kernel normalises by
@@ -141,7 +153,22 @@ class GenMultiDecay:
             if shard is not None:  # this rank's slice of the mode's events, at the indices the unsharded call uses
                 lo, n_here = shard_range(n, shard[0], shard[1])
                 mode_rng = Generator(rng.seed, rng.reserve(n) + lo)
-            if streams:
+            compiled = gen.compile() if fast else None
+            if fast and compiled.fast_ok and n_here > 0:
+                # one allocation, one C-ABI call, strided views; all modes share one sticky forbidden-decay flag
+                gen._mark_generate_called()
+                first = mode_rng.reserve(n_here)
+                if streams:
+                    with torch.cuda.stream(streams[k % n_streams]):
+                        res = compiled.generate_fast(n_here, mode_rng.seed, first, device, shared_err,
+                                                     call["normalize_weights"], call.get("_weight_scale", 1.0))
+                    for t in (res[0], next(iter(res[2].values()))):
+                        t.record_stream(main)
+                else:
+                    res = compiled.generate_fast(n_here, mode_rng.seed, first, device, shared_err,
+                                                 call["normalize_weights"], call.get("_weight_scale", 1.0))
+                out = (res[0], res[2]) if call["normalize_weights"] else res
+            elif streams:
                 with torch.cuda.stream(streams[k % n_streams]):
                     out = gen.generate(n_here, seed=mode_rng, _deferred_checks=checks, **call, **kwargs)
                 for t in (out[0], next(iter(out[-1].values()))):

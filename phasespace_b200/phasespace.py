@@ -161,6 +161,8 @@ class CompiledDecay:
         # the plain call of generate(): no per-event failure mode, no Python mass functions, nothing forbidden
         self.plain_ok = (not self.has_resonances and not self.top_is_resonance and self.n_user == 0
                          and self._static_forbidden is None)
+        # generate_fast: masses fixed or sampled in the kernel, a top particle that can decay at rest
+        self.fast_ok = not self.top_is_resonance and self.n_user == 0 and self._static_forbidden is None
         self._slot_items = tuple((name, self.slots[name]) for name in self.names)
         self._generate_c = _lib.lib.ps_generate
 
@@ -247,6 +249,29 @@ class CompiledDecay:
         # one view per output straight off the buffer (as_strided: half the cost of slicing, reshaping and indexing)
         plane = 4 * n
         return (torch.as_strided(buf, (n,), (1,), n_part * plane),
+                {name: torch.as_strided(buf, (n, 4), (4, 1), slot * plane) for name, slot in self._slot_items})
+
+    def generate_fast(self, n: int, seed: int, first_event: int, device, err, normalize: bool = True,
+                      weight_scale: float = 1.0):
+        """The same single-allocation, single-call path for any tree whose masses are fixed or sampled in the kernel
+        (``fast_ok``), at rest: resonances set the caller's sticky ``err`` flag instead of being checked here, the weights
+        may carry ``weight_scale`` or come unnormalised with their maximum weights.  This is what ``GenMultiDecay`` issues
+        per decay mode -- dozens of small launches per call, where the general path's per-launch host work (an error flag
+        of its own, a stream context, indexed views) cost four times the kernels.
+        Returns ``(weights, weights_max | None, {name: (n, 4)})``."""
+        n_part = self.n_particles
+        extra = 1 if normalize else 2
+        buf = torch.empty(((4 * n_part + extra) * n,), dtype=torch.float64, device=device)
+        base = buf.data_ptr()
+        plane = 4 * n
+        w_ptr = base + 8 * n_part * plane
+        rc = self._generate_c(self.handle, seed, first_event, n, None, 0, None, None, w_ptr,
+                              None if normalize else w_ptr + 8 * n, base, plane, None, err.data_ptr(),
+                              _lib.PS_GEN_NORMALIZE if normalize else 0, _raw_current_stream(device.index), weight_scale)
+        if rc:
+            _lib.check(rc)
+        return (torch.as_strided(buf, (n,), (1,), n_part * plane),
+                None if normalize else torch.as_strided(buf, (n,), (1,), n_part * plane + n),
                 {name: torch.as_strided(buf, (n, 4), (4, 1), slot * plane) for name, slot in self._slot_items})
 
     # ------------------------------------------------------------------ the one C-ABI call

@@ -200,3 +200,39 @@ def test_sharded_multidecay_needs_a_process_group_for_a_global_maximum():
         container.generate_sharded(2000, seed=3, boost_to=boost, rank=0, world=2)
     with pytest.raises(ValueError):
         container.generate_sharded(2000, seed=3, boost_to=boost.expand(2000, 4), rank=0, world=2)
+
+
+def test_fast_path_and_side_streams_give_the_same_events():
+    """GenMultiDecay issues its modes through CompiledDecay.generate_fast (one allocation, one C-ABI call, one shared
+    forbidden-decay flag) on the current stream for small calls and fanned out over side streams for large ones; the
+    general per-mode path (any extra keyword) and both stream layouts must give identical events.  A forbidden mode is
+    still reported through the shared flag."""
+    container = GenMultiDecay.from_dict(example_decay_chains.dstarplus_big_decay, tolerance=1e-10)
+    n = 30_011
+    w_fast, ev_fast = container.generate(n, seed=21)
+    w_gen, ev_gen = container.generate(n, seed=21, exact=False)  # a keyword: the general path
+    streamed = GenMultiDecay.from_dict(example_decay_chains.dstarplus_big_decay, tolerance=1e-10)
+    streamed.MIN_EVENTS_FOR_STREAMS = 0
+    w_st, ev_st = streamed.generate(n, seed=21)
+    w3_fast, mw_fast, _ = container.generate(n, normalize_weights=False, seed=22)
+    w3_gen, mw_gen, _ = container.generate(n, normalize_weights=False, seed=22, exact=False)
+    assert len(w_fast) == len(w_gen) == len(w_st) > 3
+    for k in range(len(w_fast)):
+        assert torch.equal(w_fast[k], w_gen[k]) and torch.equal(w_fast[k], w_st[k])
+        for name in ev_gen[k]:
+            assert torch.equal(ev_fast[k][name], ev_gen[k][name]) and torch.equal(ev_fast[k][name], ev_st[k][name])
+    assert len(w3_fast) == len(w3_gen) == len(mw_fast) == len(mw_gen) > 3
+    for k in range(len(w3_fast)):
+        assert torch.equal(w3_fast[k], w3_gen[k]) and torch.equal(mw_fast[k], mw_gen[k])
+    # a resonance that leaves no room for its sibling: forbidden in (nearly) every event, flagged by the kernel
+    from phasespace_b200.fromdecay import mass_functions as mf
+    from phasespace_b200.phasespace import ForbiddenDecayError
+
+    bad = phasespace.GenParticle("A", 1000.0).set_children(
+        phasespace.GenParticle("R1", mf.gauss_factory(990.0, 1.0)).set_children(
+            phasespace.GenParticle("a", 100.0), phasespace.GenParticle("b", 100.0)),
+        phasespace.GenParticle("R2", mf.gauss_factory(500.0, 1.0)).set_children(
+            phasespace.GenParticle("c", 100.0), phasespace.GenParticle("d", 100.0)))
+    good = phasespace.GenParticle("B", 1000.0).set_children(phasespace.GenParticle("e", 100.0), phasespace.GenParticle("f", 100.0))
+    with pytest.raises(ForbiddenDecayError):
+        GenMultiDecay([(0.5, good), (0.5, bad)]).generate(1000, seed=1)
