@@ -387,8 +387,21 @@ def run_b200(args, rank, local_rank, world):
         c1 = d1.compile()
         slabs = [{"weights": torch.empty((n1,), dtype=torch.float64, device=device),
                   "particles": torch.empty((2, n1, 4), dtype=torch.float64, device=device)} for _ in range(4)]
-        ms, clk = timed_launches(lambda k: c1.launch(n1, seed=args.seed, first_event=rank * n1, out=slabs[k % 4], err=err),
-                                 reps=2000, warmup=20)
+        # straight through the C ABI with the argument lists built beforehand (~3 us of host time per launch): the
+        # Python-level CompiledDecay.launch costs 9-15 us per call depending on the host, which on a slow host is MORE
+        # than this kernel lasts and would turn the figure into a host time
+        raw_stream = stream.cuda_stream
+        calls = [(c1.handle, args.seed, rank * n1, n1, None, 0, None, None, sl["weights"].data_ptr(), None,
+                  sl["particles"].data_ptr(), 4 * n1, None, err.data_ptr(), _lib.PS_GEN_NORMALIZE, raw_stream, 1.0)
+                 for sl in slabs]
+        ps_generate = _lib.lib.ps_generate
+
+        def launch1(k):
+            rc = ps_generate(*calls[k % 4])
+            if rc:
+                _lib.check(rc)
+
+        ms, clk = timed_launches(launch1, reps=2000, warmup=20)
         ev_s = world * n1 / (ms * 1e-3)
         entry = {"workload": "B0->K pi two-body nbody_decay(5279.65, [139.57018, 493.677]), n_events=1e6 per call, "
                              "normalize_weights=True", "events_per_gpu_per_launch": n1, "kernel_ms": ms,
@@ -396,7 +409,8 @@ def run_b200(args, rank, local_rank, world):
                  "l2": "72 MB of outputs per launch fit in the 126 MB L2: launches rotate over four output slabs (288 MB)",
                  "note": "a 1e6-event launch writes 72 MB (10 us at full bandwidth); the rest is the gap between two kernels "
                          "of a stream and the ramp of the grid, which programmatic dependent launch (launches of at most "
-                         "2^21 events) partly hides; the Python launch loop itself costs ~9 us per call"}
+                         "2^21 events) partly hides; launched straight through the C ABI (ps_generate with prebuilt argument "
+                         "lists, ~3 us of host time per call) so that the figure is the kernel's, not the host's"}
         # the reference benchmark's protocol (benchmark/bench_phasespace.py:109-133): generate(1e6) per call through the
         # public API (allocation of the outputs included), 1 warm-up + 10 timed calls
         def do_run(k):  # benchmark/bench_phasespace.py:131-133: the result is returned and dropped
