@@ -538,7 +538,7 @@ class GenParticle:
         if (boost_to is None and normalize_weights and debug_uniforms is None and not as_vectors and not exact
                 and _weight_scale == 1.0 and n_events > 0):
             compiled = self._compiled
-            if compiled is not None and compiled.epoch == _TREE_EPOCH and compiled.plain_ok:
+            if compiled is not None and compiled.epoch == _TREE_EPOCH and compiled.plain_ok and self._generate_called:
                 return compiled.generate_plain(n_events, rng.seed, rng.reserve(n_events), device)
         if boost_to is not None:
             boost_to = _convert_boost(boost_to, device)
@@ -608,9 +608,11 @@ class GenParticle:
             raise ForbiddenDecayError(f"Forbidden decay (particle {compiled._static_forbidden})")
         boost_rows = 0
         if boost_to is not None:
-            boost_to = process_list_to_tensor(boost_to, device="cpu")
+            boost_to = _convert_boost(boost_to, "cpu")
             boost_to = boost_to.reshape(1, -1) if boost_to.ndim == 1 else boost_to
-            if boost_to.shape[0] not in (n_events, 1) or boost_to.shape[1] != 4:
+            if boost_to.ndim != 2 or boost_to.shape[1] != 4:
+                raise ValueError(f"Bad shape for momentum -> {list(boost_to.shape)}")  # ps.py:257-258
+            if boost_to.shape[0] not in (n_events, 1):
                 raise ValueError(
                     f"The number of events requested ({n_events}) doesn't match the boost_to input size "
                     f"of {tuple(boost_to.shape)}"

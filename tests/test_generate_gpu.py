@@ -147,6 +147,35 @@ def test_set_children_after_generate():
         top.set_children(GenParticle("a", 1.0), GenParticle("b", 1.0))
 
 
+def test_latch_is_set_when_the_tree_was_compiled_beforehand():
+    """ps.py:318: the latch is set by the first generate() -- also when compile() was called by hand before it (the
+    plain single-call path is taken from the second call on)."""
+    top = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    top.compile()
+    assert not top._generate_called
+    first = top.generate(5, seed=3)
+    assert top._generate_called
+    again = top.generate(5, seed=3)  # the plain path
+    assert torch.equal(first[0], again[0]) and all(torch.equal(first[1][k], again[1][k]) for k in first[1])
+    with pytest.raises(RuntimeError):
+        top.set_children(GenParticle("a", 1.0), GenParticle("b", 1.0))
+
+
+def test_generate_host_takes_vector_boosts(vector_module):
+    """generate_host converts boost_to like generate (ps.py:676-695)."""
+    decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
+    n = 64
+    rng = np.random.default_rng(5)
+    p = rng.normal(size=(n, 3)) * 3000.0
+    e = np.sqrt((p * p).sum(axis=1) + B0_MASS**2)
+    booster = vector_module.array(dict(px=p[:, 0], py=p[:, 1], pz=p[:, 2], e=e))
+    w_v, parts_v = decay.generate_host(n, boost_to=booster, seed=9)
+    w_a, parts_a = decay.generate_host(n, boost_to=np.column_stack([p, e]), seed=9)
+    assert np.array_equal(w_v, w_a) and all(np.array_equal(parts_v[k], parts_a[k]) for k in parts_a)
+    with pytest.raises(ValueError, match="Bad shape"):
+        decay.generate_host(n, boost_to=np.zeros((n, 3)))
+
+
 def test_boost_to_semantics():
     decay = phasespace.nbody_decay(B0_MASS, [PION_MASS] * 3)
     n = 64
