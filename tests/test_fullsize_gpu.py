@@ -93,3 +93,40 @@ def test_config4_kstar_gamma_relbw_1e8():
     qs = torch.tensor([0.1, 0.25, 0.5, 0.75, 0.9], dtype=torch.float64, device=m_kst.device)
     got = torch.quantile(m_kst[:10_000_000], qs).cpu().numpy()
     np.testing.assert_allclose(got, np.quantile(ref, qs.cpu().numpy()), rtol=2e-3)
+
+
+def test_more_than_2_to_the_31_events_in_one_launch():
+    """Maximum sizes: the largest single launch a B200 holds -- 2**31 + 4096 two-body events, 155 GB of outputs in one
+    allocation (event counts, row offsets and plane strides are int64 throughout; 8.4e6 tiles on the covering grid).
+    Checked chunk by chunk: momentum conservation, on-shell masses, unit weights, and
+    head / middle / tail against the oracle and against separate launches at the same event indices."""
+    n = (1 << 31) + 4096
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 72 * n + (6 << 30):
+        pytest.skip(f"needs {72 * n / 1e9:.0f} GB of free HBM, the device has {free / 1e9:.0f} GB free")
+    m1, m2 = D.PION_MASS, D.KAON_MASS
+    decay = phasespace.nbody_decay(D.B0_MASS, [m1, m2])
+    comp = decay.compile()
+    w, _, p, err = comp.launch(n, seed=17)
+    assert int(err.item()) == 0
+    step = 1 << 25
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        a, b = p[0, lo:hi], p[1, lo:hi]
+        total = a + b
+        assert float(total[:, :3].abs().max()) / D.B0_MASS < 1e-12
+        assert float((total[:, 3] - D.B0_MASS).abs().max()) / D.B0_MASS < 1e-12
+        assert float((_mass(a) - m1).abs().max()) < 1e-6 and float((_mass(b) - m2).abs().max()) < 1e-6
+        assert float((w[lo:hi] - 1.0).abs().max()) < 1e-14
+        del a, b, total
+    tree = orc.flat(D.B0_MASS, [m1, m2])
+    for first in (0, (1 << 31) - 500, n - 1000):  # the middle window straddles the 32-bit boundary
+        ref_w, ref_p = orc.generate(tree, 1000, uniform_table(17, first, 1000, 2))
+        np.testing.assert_allclose(w[first:first + 1000].cpu().numpy(), ref_w, rtol=1e-12)
+        for k, name in enumerate(orc.output_names(tree)):
+            np.testing.assert_allclose(p[k, first:first + 1000].cpu().numpy(), ref_p[name], rtol=0, atol=1e-12 * D.B0_MASS)
+        w2, _, p2, _ = comp.launch(1000, seed=17, first_event=first)
+        assert torch.equal(w2, w[first:first + 1000]) and torch.equal(p2, p[:, first:first + 1000])
+    del w, p
+    torch.cuda.empty_cache()

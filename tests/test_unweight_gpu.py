@@ -156,3 +156,26 @@ def test_unweighting_parity_at_1e8_candidates():
     total = sum(parts.values())
     assert float(total[:, :3].abs().max()) / D.B0_MASS < 1e-12
     assert float((total[:, 3] - D.B0_MASS).abs().max()) / D.B0_MASS < 1e-12
+
+
+def test_more_than_2_to_the_32_candidates_in_one_call():
+    """Maximum sizes: one call over 2**32 + 12345 candidates (event counts and indices are int64 throughout: 512 MB of
+    mask bits, 1.7e7 tiles, 8193 scan segments).  A loose bound keeps the accepted sample at a few GB.  The ordered
+    list reaches past 2**32 and equals the lists of two unequal chunks of the same range, weights and events included."""
+    n, seed, first, w_bound = (1 << 32) + 12345, 11, 3, 40.0
+    decay = phasespace.nbody_decay(D.B0_MASS, [D.PION_MASS] * 3)
+    parts, index, weights = generate_unweighted(decay, n, seed, w_bound=w_bound, first_event=first)
+    n_acc = index.numel()
+    assert abs(n_acc / n - 0.27 / w_bound) < 0.02 / w_bound  # mean normalised weight of the flat three-body decay
+    assert bool((index[1:] > index[:-1]).all())
+    assert int(index[0]) >= first and int(index[-1]) < first + n and int(index[-1]) - first > (1 << 32) - 100_000
+    assert int((index - first >= (1 << 32)).sum()) > 0  # the tail beyond the 32-bit range is there
+    assert float(weights.max()) <= 1.0 and float(weights.min()) > 0.0
+    cut = (1 << 31) + 777
+    pa, ia, wa = generate_unweighted(decay, cut, seed, w_bound=w_bound, first_event=first)
+    pb, ib, wb = generate_unweighted(decay, n - cut, seed, w_bound=w_bound, first_event=first + cut)
+    assert ia.numel() + ib.numel() == n_acc
+    assert torch.equal(index[:ia.numel()], ia) and torch.equal(index[ia.numel():], ib)
+    assert torch.equal(weights[:ia.numel()], wa) and torch.equal(weights[ia.numel():], wb)
+    for name in parts:
+        assert torch.equal(parts[name][:ia.numel()], pa[name]) and torch.equal(parts[name][ia.numel():], pb[name])
