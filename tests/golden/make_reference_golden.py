@@ -173,7 +173,62 @@ def build(ref):
             ref.GenParticle("c", PION_MASS), ref.GenParticle("d", PION_MASS), ref.GenParticle("e", 0.0)),
         ref.GenParticle("f", 105.6583755))
     run("two_branches", chain, n, (3 * 3 - 4) + 2 + (3 * 3 - 4), masses_store=store)
+
+    # ---- second batch (appended: the draws of the cases above are unchanged) ----
+    # the kernel switches from the step-by-step formulation to one accumulated Lorentz matrix at nine children
+    for nb in (8, 9):
+        run(f"flat{nb}", ref.nbody_decay(B0_MASS, [PION_MASS] * nb), n, n_draws_flat(nb))
+    run("flat2_boost", ref.nbody_decay(B0_MASS, [PION_MASS, KAON_MASS]), n, 0 + 2, boost=boost_rows(n, 10))
+    run("flat3_massless", ref.nbody_decay(100.0, [0.0, 0.0, 0.0]), n, n_draws_flat(3))
+    run("kstar_gamma_fixed_boost_one_row", kstar_gamma(KSTARZ_MASS), n, 4, boost=boost_rows(1, 11))
+
+    # tests/helpers/decays.py:47-76 with every mass fixed: recurse_w_max over two levels of fixed-mass intermediates
+    k1_fixed = ref.GenParticle("B+", B0_MASS).set_children(
+        ref.GenParticle("K1+", K1_MASS).set_children(
+            ref.GenParticle("K*0", KSTARZ_MASS).set_children(
+                ref.GenParticle("K+", KAON_MASS), ref.GenParticle("pi-", PION_MASS)),
+            ref.GenParticle("pi+", PION_MASS)),
+        ref.GenParticle("gamma", 0.0))
+    run("k1_gamma_fixed", k1_fixed, n, 6)
+    run("k1_gamma_fixed_boost", k1_fixed_copy(ref), n, 6, boost=boost_rows(n, 12))
+
+    # a nine-body decay below the top particle (its products are boosted by the parent afterwards), with and without
+    # a per-event boost of the whole event
+    def nine_below(store_, frac_):
+        return ref.GenParticle("A", 12000.0).set_children(
+            ref.GenParticle("X", recording_mass(store_, "X", frac_)).set_children(
+                *[ref.GenParticle(f"x{i}", PION_MASS) for i in range(9)]),
+            ref.GenParticle("g", 0.0), ref.GenParticle("h", 938.272))
+
+    f3 = np.clip(rng.beta(4.0, 4.0, n), 1e-6, 1.0)
+    store = {}
+    run("nine_body_subdecay", nine_below(store, f3), n, n_draws_flat(3) + n_draws_flat(9), masses_store=store)
+    store = {}
+    p = np.random.default_rng(13).normal(0.0, 30000.0, (n, 3))
+    boost_a = np.concatenate([p, np.sqrt((p * p).sum(1, keepdims=True) + 12000.0**2)], axis=1)
+    run("nine_body_subdecay_boost", nine_below(store, f3), n, n_draws_flat(3) + n_draws_flat(9), boost=boost_a,
+        masses_store=store)
+
+    # three levels, three-body decays inside: top -> R1(-> R2(-> a b c) d e) f, R1 callable, R2 fixed
+    store = {}
+    deep = ref.GenParticle("T", 9000.0).set_children(
+        ref.GenParticle("R1", recording_mass(store, "R1", f2)).set_children(
+            ref.GenParticle("R2", 2000.0).set_children(
+                ref.GenParticle("a", PION_MASS), ref.GenParticle("b", KAON_MASS), ref.GenParticle("c", 0.0)),
+            ref.GenParticle("d", PION_MASS), ref.GenParticle("e", 105.6583755)),
+        ref.GenParticle("f", 938.272))
+    run("three_levels_three_body", deep, n, 2 + n_draws_flat(3) + n_draws_flat(3), masses_store=store)
     return out
+
+
+def k1_fixed_copy(ref):
+    """A second instance of the fixed-mass K1 chain (a GenParticle generates with one boost_to setting per trace)."""
+    return ref.GenParticle("B+", B0_MASS).set_children(
+        ref.GenParticle("K1+", K1_MASS).set_children(
+            ref.GenParticle("K*0", KSTARZ_MASS).set_children(
+                ref.GenParticle("K+", KAON_MASS), ref.GenParticle("pi-", PION_MASS)),
+            ref.GenParticle("pi+", PION_MASS)),
+        ref.GenParticle("gamma", 0.0))
 
 
 def main():

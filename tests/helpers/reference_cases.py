@@ -22,6 +22,13 @@ def _kstar_gamma(kind, mass=D.KSTARZ_MASS):
         ("K*0", mass, kind, 0.0, [_leaf("K+", D.KAON_MASS), _leaf("pi-", D.PION_MASS)]), _leaf("gamma", 0.0)])
 
 
+_K1_FIXED = ("B+", D.B0_MASS, "fixed", 0.0, [
+    ("K1+", D.K1_MASS, "fixed", 0.0, [
+        ("K*0", D.KSTARZ_MASS, "fixed", 0.0, [_leaf("K+", D.KAON_MASS), _leaf("pi-", D.PION_MASS)]), _leaf("pi+", D.PION_MASS)]),
+    _leaf("gamma", 0.0)])
+_NINE_BELOW = ("A", 12000.0, "fixed", 0.0, [
+    ("X", 0.0, "user", 0.0, [_leaf(f"x{i}", D.PION_MASS) for i in range(9)]), _leaf("g", 0.0), _leaf("h", 938.272)])
+
 CASES = {
     "flat2": D.flat_desc(2),
     "flat3": D.flat_desc(3),
@@ -41,6 +48,21 @@ CASES = {
         ("X", 1500.0, "fixed", 0.0, [_leaf("a", D.PION_MASS), _leaf("b", D.KAON_MASS)]),
         ("Y", 0.0, "user", 0.0, [_leaf("c", D.PION_MASS), _leaf("d", D.PION_MASS), _leaf("e", 0.0)]),
         _leaf("f", MUON_MASS)]),
+    # second batch
+    "flat8": D.flat_desc(8),
+    "flat9": D.flat_desc(9),
+    "flat2_boost": D.flat_desc(2, masses=[D.PION_MASS, D.KAON_MASS]),
+    "flat3_massless": D.flat_desc(3, top=100.0, masses=[0.0, 0.0, 0.0]),
+    "kstar_gamma_fixed_boost_one_row": _kstar_gamma("fixed"),
+    "k1_gamma_fixed": _K1_FIXED,
+    "k1_gamma_fixed_boost": _K1_FIXED,
+    "nine_body_subdecay": _NINE_BELOW,
+    "nine_body_subdecay_boost": _NINE_BELOW,
+    "three_levels_three_body": ("T", 9000.0, "fixed", 0.0, [
+        ("R1", 0.0, "user", 0.0, [
+            ("R2", 2000.0, "fixed", 0.0, [_leaf("a", D.PION_MASS), _leaf("b", D.KAON_MASS), _leaf("c", 0.0)]),
+            _leaf("d", D.PION_MASS), _leaf("e", MUON_MASS)]),
+        _leaf("f", 938.272)]),
 }
 
 
